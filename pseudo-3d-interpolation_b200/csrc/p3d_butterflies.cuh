@@ -1,0 +1,172 @@
+// Radix butterflies for the Stockham passes (registers only, fully unrolled).
+//
+// All trigonometric constants are produced by constexpr polynomial evaluation in double
+// and folded by the compiler after unrolling (check: no DFMA/MUFU.SIN in the SASS of the
+// FFT kernels).  DIR = -1 is the forward transform exp(-2 pi i jk/N), DIR = +1 the
+// (unscaled) inverse.  T is float or double.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace p3d {
+
+template <typename T> struct Cx { T x, y; };
+template <> struct __align__(8)  Cx<float>  { float x, y; };
+template <> struct __align__(16) Cx<double> { double x, y; };
+
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cmake(T a, T b) { Cx<T> r; r.x = a; r.y = b; return r; }
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return cmake<T>(a.x + b.x, a.y + b.y); }
+template <typename T> __host__ __device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) { return cmake<T>(a.x - b.x, a.y - b.y); }
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
+    return cmake<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cmulc(Cx<T> a, Cx<T> b) {
+    return cmake<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cscale(Cx<T> a, T s) { return cmake<T>(a.x * s, a.y * s); }
+// multiply by DIR * i  (DIR=-1: -i ; DIR=+1: +i)
+template <int DIR, typename T> __host__ __device__ __forceinline__ Cx<T> cmul_i(Cx<T> a) {
+    return DIR < 0 ? cmake<T>(a.y, -a.x) : cmake<T>(-a.y, a.x);
+}
+
+// ---------------------------------------------------------------------------------------
+// constexpr trigonometry: cos(2 pi m / n), sin(2 pi m / n) for integer m, n
+// ---------------------------------------------------------------------------------------
+__host__ __device__ constexpr double cx_sin_poly(double x) {   // |x| <= pi/4
+    double x2 = x * x;
+    return x * (1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880 + x2 * (-1.0 / 39916800 +
+           x2 * (1.0 / 6227020800.0 + x2 * (-1.0 / 1307674368000.0))))))));
+}
+__host__ __device__ constexpr double cx_cos_poly(double x) {   // |x| <= pi/4
+    double x2 = x * x;
+    return 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800 +
+           x2 * (1.0 / 479001600.0 + x2 * (-1.0 / 87178291200.0 + x2 * (1.0 / 20922789888000.0))))))));
+}
+constexpr double CX_PI = 3.141592653589793238462643383279502884;
+
+// angle = 2 pi m / n reduced with exact integer arithmetic to an octant
+__host__ __device__ constexpr double cx_cos2pi(int m, int n) {
+    m %= n; if (m < 0) m += n;
+    // use cos symmetry about pi: m -> n - m
+    if (2 * m > n) m = n - m;                 // now angle in [0, pi]
+    bool neg = false;
+    // angle > pi/2  <=> 4m > n : cos(a) = -cos(pi - a), pi - a = 2 pi (n/2 - m)/n = 2 pi (n - 2m)/(2n)
+    int num = m, den = n;                     // angle = 2 pi num/den
+    if (4 * m > n) { neg = true; num = n - 2 * m; den = 2 * n; }   // now angle in [0, pi/2]
+    // angle > pi/4 <=> 8 num > den : cos(a) = sin(pi/2 - a) = sin(2 pi (den - 4 num)/(4 den))
+    double r = 0.0;
+    if (8 * num > den) r = cx_sin_poly(2.0 * CX_PI * (double)(den - 4 * num) / (4.0 * (double)den));
+    else               r = cx_cos_poly(2.0 * CX_PI * (double)num / (double)den);
+    return neg ? -r : r;
+}
+__host__ __device__ constexpr double cx_sin2pi(int m, int n) {
+    // sin(2 pi m/n) = cos(2 pi m/n - pi/2) = cos(2 pi (4m - n)/(4n))
+    return cx_cos2pi(4 * m - n, 4 * n);
+}
+
+// W_n^m for direction DIR: exp(DIR * 2 pi i m / n)
+template <int DIR, typename T> __host__ __device__ __forceinline__ Cx<T> cx_w(int m, int n) {
+    return cmake<T>((T)cx_cos2pi(m, n), (T)((double)DIR * cx_sin2pi(m, n)));
+}
+
+// ---------------------------------------------------------------------------------------
+// butterflies: in-place DFT of v[0..R-1]
+// ---------------------------------------------------------------------------------------
+template <int R, int DIR, typename T> struct Bfly;
+
+template <int DIR, typename T> struct Bfly<1, DIR, T> {
+    __device__ __forceinline__ static void run(Cx<T>* v) {}
+};
+
+template <int DIR, typename T> struct Bfly<2, DIR, T> {
+    __device__ __forceinline__ static void run(Cx<T>* v) {
+        Cx<T> a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    }
+};
+
+template <int DIR, typename T> struct Bfly<4, DIR, T> {
+    __device__ __forceinline__ static void run(Cx<T>* v) {
+        Cx<T> a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+        Cx<T> c = cadd(v[1], v[3]), d = cmul_i<DIR>(csub(v[1], v[3]));
+        v[0] = cadd(a, c); v[2] = csub(a, c);
+        v[1] = cadd(b, d); v[3] = csub(b, d);
+    }
+};
+
+// odd prime radix, symmetric form: pairs (j, P-j)
+template <int P, int DIR, typename T> struct BflyPrime {
+    __device__ __forceinline__ static void run(Cx<T>* v) {
+        constexpr int H = (P - 1) / 2;
+        Cx<T> s[H], d[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) { s[j] = cadd(v[j + 1], v[P - 1 - j]); d[j] = csub(v[j + 1], v[P - 1 - j]); }
+        Cx<T> x0 = v[0];
+        Cx<T> sum = x0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) sum = cadd(sum, s[j]);
+        v[0] = sum;
+#pragma unroll
+        for (int k = 1; k <= H; ++k) {
+            Cx<T> A = x0, B = cmake<T>(T(0), T(0));
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                const T c = (T)cx_cos2pi(j * k, P);
+                const T sn = (T)cx_sin2pi(j * k, P);
+                A.x += c * s[j - 1].x; A.y += c * s[j - 1].y;
+                B.x += sn * d[j - 1].x; B.y += sn * d[j - 1].y;
+            }
+            // forward: X[k] = A - i B, X[P-k] = A + i B ; inverse swaps
+            Cx<T> iB = cmul_i<DIR>(B);         // DIR*i*B
+            v[k] = cadd(A, iB);
+            v[P - k] = csub(A, iB);
+        }
+    }
+};
+template <int DIR, typename T> struct Bfly<3, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPrime<3, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<5, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPrime<5, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<7, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPrime<7, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<11, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPrime<11, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<13, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPrime<13, DIR, T>::run(v); } };
+
+// composite radix R = R1 * R2 (Cooley-Tukey inside registers, constant twiddles)
+//   X[k1 + R1 k2] = sum_{n2} W_R^{n2 k1} [ sum_{n1} x[R2 n1 + n2] W_R1^{n1 k1} ] W_R2^{n2 k2}
+template <int R1, int R2, int DIR, typename T> struct BflyCT {
+    __device__ __forceinline__ static void run(Cx<T>* v) {
+        constexpr int R = R1 * R2;
+        Cx<T> y[R2][R1];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) y[n2][n1] = v[R2 * n1 + n2];
+            Bfly<R1, DIR, T>::run(y[n2]);
+#pragma unroll
+            for (int k1 = 1; k1 < R1; ++k1) {
+                if (n2 == 0) continue;
+                const int m = (n2 * k1) % R;
+                // exploit trivial twiddles
+                if (4 * m == R)            y[n2][k1] = cmul_i<DIR>(y[n2][k1]);
+                else if (2 * m == R)       y[n2][k1] = cmake<T>(-y[n2][k1].x, -y[n2][k1].y);
+                else if (4 * m == 3 * R)   y[n2][k1] = cmul_i<-DIR>(y[n2][k1]);
+                else                       y[n2][k1] = cmul(y[n2][k1], cx_w<DIR, T>(m, R));
+            }
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            Cx<T> z[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) z[n2] = y[n2][k1];
+            Bfly<R2, DIR, T>::run(z);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = z[k2];
+        }
+    }
+};
+template <int DIR, typename T> struct Bfly<6, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<2, 3, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<8, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<2, 4, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<9, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<3, 3, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<10, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<2, 5, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<16, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<4, 4, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<20, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<4, 5, DIR, T>::run(v); } };
+
+}  // namespace p3d

@@ -1,0 +1,306 @@
+// POCS kernels, generic path (any slice shape): shared-memory tiles + p3d_fft_generic.cuh.
+//
+// One POCS iteration is two launches over a band of slices:
+//   k_cols_iter :  column FFT -> threshold(tau_k) -> column IFFT            (in place on W)
+//   k_rows_iter :  row IFFT -> x = alpha*d + (1-alpha*m)*y/(N1 N2) -> sum|x| -> row FFT
+// preceded once per slice by k_rows_init (row FFT of the observed slice + count_nonzero +
+// sum|d|) and k_cols_stats (column FFT + the statistics the schedule needs).
+#pragma once
+#include <stdint.h>
+#include "../../include/p3d_b200.h"
+#include "p3d_fft_generic.cuh"
+
+namespace p3d {
+
+// Per-slice statistics of the initial spectrum X0 = fft2(x) (functions/POCS.py:286-299,251-260)
+struct SliceStats {
+    unsigned long long lexmax_key;   // ordered (re, im) key of max_lex X0
+    double sumsq;                    // sum |X0|^2
+    unsigned int maxabs_bits;        // max |X0| (float bits, non-negative => ordered as uint)
+    unsigned int minabs_bits;        // min |X0|
+    unsigned long long nnz;          // count_nonzero(x)
+    unsigned long long n_cand;       // data-driven: number of candidates inside (tau_min, tau_max)
+};
+
+__host__ __device__ __forceinline__ unsigned int f32_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    unsigned int u = __float_as_uint(f);
+#else
+    unsigned int u; memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float f32_from_ordered(unsigned int u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+__host__ __device__ __forceinline__ unsigned long long lex_key(float re, float im) {
+    return ((unsigned long long)f32_ordered(re) << 32) | (unsigned long long)f32_ordered(im);
+}
+
+struct PocsGeom {
+    int n1, n2;            // rows (iline), columns (xline, contiguous)
+    int C;                 // columns per column tile
+    int RB;                // rows per row tile
+    int pitch2;            // smem pitch of a row line (>= ax2.L)
+    int slices_per_mask;   // mask index = global slice / slices_per_mask
+};
+
+template <typename T> struct BandArgs {
+    Cx<T>* W;                    // work spectrum / iterate, [band][n1][n2]
+    const Cx<T>* D;              // observed slices
+    Cx<T>* OUT;                  // result slices (also scratch for X0 in the data-driven setup)
+    const uint8_t* mask;         // [n_masks][n1][n2]
+    long long first_slice;       // global index of the band's first slice (for the mask lookup)
+    const Cx<T>* tau;            // [band][niter]
+    double* S;                   // [band][niter+1]  (S[.][0] = sum|d|, S[.][k+1] = sum|x_k|)
+    int* stop;                   // [band] 0 = active, k>0 = stopped after k iterations, -1 = all-zero slice
+    SliceStats* stats;           // [band]
+    int k, niter;
+    double eps;
+    T alpha, inv_n;
+    int write_out, last, adaptive, store_x0, accum;
+};
+
+// ---------------------------------------------------------------------------------------------
+// threshold operators with the reference's complex-tau semantics
+// ---------------------------------------------------------------------------------------------
+template <int OP, typename T>
+__device__ __forceinline__ Cx<T> apply_threshold(Cx<T> X, const T a, const T b, const T t2re, const T t2im) {
+    const T r2 = X.x * X.x + X.y * X.y;
+    if (OP == P3D_OP_HARD) {
+        const T r = sqrt(r2);
+        const bool kill = (r < a) || (r == a && b > T(0));
+        return kill ? cmake<T>(T(0), T(0)) : X;
+    } else if (OP == P3D_OP_SOFT) {
+        const T r = sqrt(r2);
+        const T inv = T(1) / r;
+        T fre = T(1) - a * inv, fim = -(b * inv);
+        const bool zero = (r == T(0)) || (fre < T(0)) || (fre == T(0) && fim < T(0));
+        if (zero) return cmake<T>(T(0), T(0));
+        return cmake<T>(X.x * fre - X.y * fim, X.x * fim + X.y * fre);
+    } else {
+        const T inv = T(1) / r2;
+        T fre = T(1) - t2re * inv, fim = -(t2im * inv);
+        const bool zero = (r2 == T(0)) || (fre < T(0)) || (fre == T(0) && fim < T(0));
+        if (zero) return cmake<T>(T(0), T(0));
+        return cmake<T>(X.x * fre - X.y * fim, X.x * fim + X.y * fre);
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned int warp_max_u32(unsigned int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned int w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned int warp_min_u32(unsigned int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned int w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+}
+
+// device-side replica of the reference's stop test (functions/POCS.py:631): iteration j = k-1
+// finished with cost_j; stop when j > 2 and cost_j < eps.  Returns true when the slice is inactive.
+__device__ __forceinline__ bool slice_stopped(int* stop, const double* S, int s, int k, int niter, double eps) {
+    const int st = stop[s];
+    if (st != 0) return true;
+    if (eps > 0.0 && k >= 4) {
+        const double sk = S[(long long)s * (niter + 1) + k], skm = S[(long long)s * (niter + 1) + k - 1];
+        const double d = sk - skm;
+        const double cost = (d * d) / (sk * sk);
+        if (cost < eps) {
+            if (threadIdx.x == 0) stop[s] = k;
+            return true;
+        }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic column kernel.  MODE 0: statistics of X0 (optionally store X0), MODE 1: iterate
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int OP>
+__global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_constant__ AxisDev<T> ax1,
+                               const __grid_constant__ BandArgs<T> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int s = blockIdx.y;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    if (MODE == 1) { if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) return; }
+
+    const int c0 = blockIdx.x * G.C;
+    const int nc = min(G.C, G.n2 - c0);
+    Cx<T>* bufA = reinterpret_cast<Cx<T>*>(smem_raw);
+    Cx<T>* bufB = bufA + (size_t)ax1.L * G.C;
+    const long long slice_off = (long long)s * G.n1 * G.n2;
+    Cx<T>* Ws = A.W + slice_off;
+
+    const int tot = G.n1 * nc;
+    for (int w = tid; w < tot; w += nth) {
+        const int i = w / nc, c = w - i * nc;
+        bufA[i * G.C + c] = Ws[(long long)i * G.n2 + c0 + c];
+    }
+    __syncthreads();
+    TileGeom tg; tg.nlines = nc; tg.line_stride = 1; tg.elem_stride = G.C; tg.line_fastest = 1;
+    Cx<T>* X = line_fft<-1, T>(bufA, bufB, tg, ax1, tid, nth);
+    Cx<T>* other = (X == bufA) ? bufB : bufA;
+
+    if (MODE == 0) {
+        unsigned long long kmax = 0ull; double ss = 0.0; unsigned int amax = 0u, amin = 0xffffffffu;
+        Cx<T>* X0s = A.OUT + slice_off;
+        for (int w = tid; w < tot; w += nth) {
+            const int i = w / nc, c = w - i * nc;
+            const Cx<T> v = X[i * G.C + c];
+            const unsigned long long key = lex_key((float)v.x, (float)v.y);
+            kmax = key > kmax ? key : kmax;
+            const float r2 = (float)(v.x * v.x + v.y * v.y);
+            ss += (double)r2;
+            const unsigned int rb = __float_as_uint(sqrtf(r2));
+            amax = rb > amax ? rb : amax; amin = rb < amin ? rb : amin;
+            if (A.store_x0) X0s[(long long)i * G.n2 + c0 + c] = v;
+        }
+        kmax = warp_max_u64(kmax); ss = warp_sum(ss); amax = warp_max_u32(amax); amin = warp_min_u32(amin);
+        if ((tid & 31) == 0) {
+            atomicMax(&A.stats[s].lexmax_key, kmax);
+            atomicAdd(&A.stats[s].sumsq, ss);
+            atomicMax(&A.stats[s].maxabs_bits, amax);
+            atomicMin(&A.stats[s].minabs_bits, amin);
+        }
+        return;
+    }
+
+    // threshold in place
+    const Cx<T> tau = A.tau[(long long)s * A.niter + A.k];
+    const T a = tau.x, b = tau.y;
+    const T t2re = a * a - b * b, t2im = T(2) * a * b;
+    for (int w = tid; w < tot; w += nth) {
+        const int i = w / nc, c = w - i * nc;
+        Cx<T>* p = X + i * G.C + c;
+        *p = apply_threshold<OP, T>(*p, a, b, t2re, t2im);
+    }
+    __syncthreads();
+    Cx<T>* Y = line_fft<+1, T>(X, other, tg, ax1, tid, nth);
+    for (int w = tid; w < tot; w += nth) {
+        const int i = w / nc, c = w - i * nc;
+        Ws[(long long)i * G.n2 + c0 + c] = Y[i * G.C + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic row kernel.  MODE 0: init (row FFT of d, nnz, sum|d|), MODE 1: iterate
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void k_rows_generic(const __grid_constant__ PocsGeom G, const __grid_constant__ AxisDev<T> ax2,
+                               const __grid_constant__ BandArgs<T> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_s[32];
+    __shared__ unsigned long long red_n[32];
+    const int s = blockIdx.y;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    if (MODE == 1) { if (A.stop[s] != 0) return; }
+    if (MODE == 0 && A.adaptive) { if (A.stop[s] != 0) return; }
+
+    const int r0 = blockIdx.x * G.RB;
+    const int nr = min(G.RB, G.n1 - r0);
+    Cx<T>* bufA = reinterpret_cast<Cx<T>*>(smem_raw);
+    Cx<T>* bufB = bufA + (size_t)G.pitch2 * G.RB;
+    const long long slice_off = (long long)s * G.n1 * G.n2;
+    const long long row_off = slice_off + (long long)r0 * G.n2;
+    const long long mask_off = ((A.first_slice + s) / G.slices_per_mask) * (long long)G.n1 * G.n2 + (long long)r0 * G.n2;
+    const int tot = nr * G.n2;
+    TileGeom tg; tg.nlines = nr; tg.line_stride = G.pitch2; tg.elem_stride = 1; tg.line_fastest = 0;
+
+    double part = 0.0;
+    unsigned long long nnz = 0ull;
+    Cx<T>* cur;
+
+    if (MODE == 0) {
+        for (int w = tid; w < tot; w += nth) {
+            const int rr = w / G.n2, j = w - rr * G.n2;
+            Cx<T> d = A.D[row_off + (long long)rr * G.n2 + j];
+            if (!A.adaptive) {
+                nnz += (d.x != T(0) || d.y != T(0)) ? 1ull : 0ull;
+                part += (double)sqrt(d.x * d.x + d.y * d.y);
+            } else {
+                // APOCS prologue with x_old = x (functions/POCS.py:572-575)
+                const T m = (T)A.mask[mask_off + (long long)rr * G.n2 + j];
+                const T keep = T(1) - A.alpha * m;
+                Cx<T> xt = cmake<T>(A.alpha * d.x + keep * d.x, A.alpha * d.y + keep * d.y);
+                const T om = T(1) - A.alpha;
+                d = cmake<T>(xt.x + om * (d.x - m * d.x), xt.y + om * (d.y - m * d.y));
+            }
+            bufA[rr * G.pitch2 + j] = d;
+        }
+        cur = bufA;
+    } else {
+        for (int w = tid; w < tot; w += nth) {
+            const int rr = w / G.n2, j = w - rr * G.n2;
+            bufA[rr * G.pitch2 + j] = A.W[row_off + (long long)rr * G.n2 + j];
+        }
+        __syncthreads();
+        cur = line_fft<+1, T>(bufA, bufB, tg, ax2, tid, nth);
+        // re-insertion: x = alpha*d + (1 - alpha*m) * y / (N1 N2)      (functions/POCS.py:616-619)
+        for (int w = tid; w < tot; w += nth) {
+            const int rr = w / G.n2, j = w - rr * G.n2;
+            const long long g = (long long)rr * G.n2 + j;
+            const Cx<T> d = A.D[row_off + g];
+            const T m = (T)A.mask[mask_off + g];
+            const T coef = (T(1) - A.alpha * m) * A.inv_n;
+            const Cx<T> y = cur[rr * G.pitch2 + j];
+            Cx<T> x = cmake<T>(fma(coef, y.x, A.alpha * d.x), fma(coef, y.y, A.alpha * d.y));
+            part += (double)sqrt(x.x * x.x + x.y * x.y);
+            if (A.write_out) A.OUT[row_off + g] = x;
+            if (A.adaptive) {
+                const T keep = T(1) - A.alpha * m;
+                Cx<T> xt = cmake<T>(A.alpha * d.x + keep * x.x, A.alpha * d.y + keep * x.y);
+                const T om = T(1) - A.alpha;
+                x = cmake<T>(xt.x + om * (d.x - m * x.x), xt.y + om * (d.y - m * x.y));
+            }
+            cur[rr * G.pitch2 + j] = x;
+        }
+    }
+    // block reduction of sum|.| (and nnz)
+    part = warp_sum(part);
+    if (MODE == 0) { for (int o = 16; o > 0; o >>= 1) nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
+    if ((tid & 31) == 0) { red_s[tid >> 5] = part; red_n[tid >> 5] = nnz; }
+    __syncthreads();
+    if (tid < 32) {
+        const int nw = (nth + 31) >> 5;
+        double v = tid < nw ? red_s[tid] : 0.0;
+        unsigned long long c = tid < nw ? red_n[tid] : 0ull;
+        v = warp_sum(v);
+        if (MODE == 0) { for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o); }
+        if (tid == 0) {
+            if (MODE == 0) {
+                if (A.accum) {
+                    atomicAdd(&A.S[(long long)s * (A.niter + 1)], v);
+                    atomicAdd(&A.stats[s].nnz, c);
+                }
+            } else {
+                atomicAdd(&A.S[(long long)s * (A.niter + 1) + A.k + 1], v);
+            }
+        }
+    }
+    if (MODE == 1 && A.last) return;
+    Cx<T>* other = (cur == bufA) ? bufB : bufA;
+    Cx<T>* X = line_fft<-1, T>(cur, other, tg, ax2, tid, nth);
+    for (int w = tid; w < tot; w += nth) {
+        const int rr = w / G.n2, j = w - rr * G.n2;
+        A.W[row_off + (long long)rr * G.n2 + j] = X[rr * G.pitch2 + j];
+    }
+}
+
+}  // namespace p3d

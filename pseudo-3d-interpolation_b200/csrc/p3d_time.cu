@@ -1,0 +1,224 @@
+// Kernel 1: batched trace rfft / irfft along the time axis of a (nt, n_traces) cube.
+//
+// The time axis is the SLOWEST axis of the (twt, iline, xline) cube, so a trace is a strided
+// column.  A CTA takes a tile of 2C adjacent traces (contiguous 8C bytes per time sample),
+// packs two real traces into one complex line (z = x_a + i x_b), runs one complex FFT per
+// pair in shared memory and separates the two spectra with the Hermitian identities; the
+// epilogue applies dt * exp(-2 pi i f_k t0) * window[k] and writes the slice-major
+// (nf, n_traces) complex64 layout the POCS kernels consume.  The inverse does the mirror
+// image (phase, Hermitian symmetrisation = "take the real part", packed complex IFFT).
+#include "p3d_host.h"
+
+#include <cmath>
+#include <cstring>
+
+using namespace p3d;
+
+namespace {
+
+struct TimeGeom {
+    long long nt;          // samples present in the time cube (forward: input; inverse: output rows)
+    long long nf;          // frequency rows
+    long long ntr;         // traces
+    int nfft;
+    int C;                 // complex lines (trace pairs) per tile
+    int compute_real;
+    int ascending;
+};
+
+// forward: x (nt, ntr) float32 -> F (nf, ntr) complex64
+__global__ void k_time_fwd(const __grid_constant__ TimeGeom G, const __grid_constant__ AxisDev<float> ax,
+                           const float* __restrict__ x, Cx<float>* __restrict__ F, const Cx<float>* __restrict__ phase) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    Cx<float>* bufA = reinterpret_cast<Cx<float>*>(smem_raw);
+    Cx<float>* bufB = bufA + (size_t)ax.L * G.C;
+    const long long tr0 = (long long)blockIdx.x * 2 * G.C;         // first trace of the tile
+    const int ntr_tile = (int)min((long long)2 * G.C, G.ntr - tr0);
+    const int nc = (ntr_tile + 1) / 2;
+    const int N = G.nfft;
+
+    // load + pack (zero beyond nt and beyond the last trace)
+    const int tot = N * nc;
+    for (int w = tid; w < tot; w += nth) {
+        const int n = w / nc, c = w - n * nc;
+        float a = 0.f, b = 0.f;
+        if (n < G.nt) {
+            const long long base = (long long)n * G.ntr + tr0 + 2 * c;
+            a = x[base];
+            if (2 * c + 1 < ntr_tile) b = x[base + 1];
+        }
+        bufA[n * G.C + c] = cmake<float>(a, b);
+    }
+    __syncthreads();
+    TileGeom tg; tg.nlines = nc; tg.line_stride = 1; tg.elem_stride = G.C; tg.line_fastest = 1;
+    Cx<float>* Z = line_fft<-1, float>(bufA, bufB, tg, ax, tid, nth);
+
+    // separate the two real traces: Xa[k] = (Z[k] + conj Z[N-k]) / 2, Xb[k] = (Z[k] - conj Z[N-k]) / (2i)
+    const int totf = (int)G.nf * nc;
+    for (int w = tid; w < totf; w += nth) {
+        const int k = w / nc, c = w - k * nc;
+        const int km = (k == 0) ? 0 : N - k;
+        const Cx<float> z1 = Z[k * G.C + c], z2 = Z[km * G.C + c];
+        const Cx<float> xa = cmake<float>(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+        const Cx<float> xb = cmake<float>(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+        const Cx<float> ph = phase[k];
+        const long long o = (long long)k * G.ntr + tr0 + 2 * c;
+        F[o] = cmul(xa, ph);
+        if (2 * c + 1 < ntr_tile) F[o + 1] = cmul(xb, ph);
+    }
+}
+
+// inverse: F (nf, ntr) complex64 -> x (nt_out, ntr) float32
+__global__ void k_time_inv(const __grid_constant__ TimeGeom G, const __grid_constant__ AxisDev<float> ax,
+                           const Cx<float>* __restrict__ F, float* __restrict__ x, const Cx<float>* __restrict__ phase) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    Cx<float>* bufA = reinterpret_cast<Cx<float>*>(smem_raw);
+    Cx<float>* bufB = bufA + (size_t)ax.L * G.C;
+    const long long tr0 = (long long)blockIdx.x * 2 * G.C;
+    const int ntr_tile = (int)min((long long)2 * G.C, G.ntr - tr0);
+    const int nc = (ntr_tile + 1) / 2;
+    const int N = G.nfft;
+    const int half = N / 2;
+
+    // stage G_a[k] * phase[k] into bufA and G_b[k] * phase[k] into bufB, indexed by FFT bin k
+    const int nbins = G.compute_real ? half + 1 : N;
+    const int tot = nbins * nc;
+    for (int w = tid; w < tot; w += nth) {
+        const int k = w / nc, c = w - k * nc;
+        // row of the input that holds bin k
+        long long row = k;
+        if (!G.compute_real && G.ascending) row = (k + half) % N;
+        const Cx<float> ph = phase[k];
+        const long long o = row * G.ntr + tr0 + 2 * c;
+        Cx<float> ga = cmul(F[o], ph);
+        Cx<float> gb = cmake<float>(0.f, 0.f);
+        if (2 * c + 1 < ntr_tile) gb = cmul(F[o + 1], ph);
+        bufA[k * G.C + c] = ga;
+        bufB[k * G.C + c] = gb;
+    }
+    __syncthreads();
+    // Hermitian symmetrisation (real part of the inverse transform) + packing H = Ha + i Hb;
+    // one thread owns the pair (k, N-k)
+    const int totp = (half + 1) * nc;
+    for (int w = tid; w < totp; w += nth) {
+        const int k = w / nc, c = w - k * nc;
+        const int km = (k == 0) ? 0 : N - k;
+        Cx<float> a1 = bufA[k * G.C + c], b1 = bufB[k * G.C + c];
+        Cx<float> ha, hb;        // symmetrised spectra at bin k
+        if (G.compute_real) {
+            // irfft semantics: bins 0..N/2 given, imaginary part of DC / Nyquist ignored
+            ha = a1; hb = b1;
+            if (k == 0 || k == half) { ha.y = 0.f; hb.y = 0.f; }
+        } else {
+            const Cx<float> a2 = bufA[km * G.C + c], b2 = bufB[km * G.C + c];
+            ha = cmake<float>(0.5f * (a1.x + a2.x), 0.5f * (a1.y - a2.y));
+            hb = cmake<float>(0.5f * (b1.x + b2.x), 0.5f * (b1.y - b2.y));
+        }
+        // H[k] = ha + i hb ; H[N-k] = conj(ha) + i conj(hb)
+        bufA[k * G.C + c] = cmake<float>(ha.x - hb.y, ha.y + hb.x);
+        if (km != k) bufA[km * G.C + c] = cmake<float>(ha.x + hb.y, hb.x - ha.y);
+    }
+    __syncthreads();
+    TileGeom tg; tg.nlines = nc; tg.line_stride = 1; tg.elem_stride = G.C; tg.line_fastest = 1;
+    Cx<float>* Z = line_fft<+1, float>(bufA, bufB, tg, ax, tid, nth);
+    const int toto = (int)G.nt * nc;
+    for (int w = tid; w < toto; w += nth) {
+        const int n = w / nc, c = w - n * nc;
+        const Cx<float> z = Z[n * G.C + c];
+        const long long o = (long long)n * G.ntr + tr0 + 2 * c;
+        x[o] = z.x;
+        if (2 * c + 1 < ntr_tile) x[o + 1] = z.y;
+    }
+}
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+int choose_cols(int L, size_t smem_optin) {
+    int C = 8;
+    while (C > 1 && (size_t)2 * L * C * sizeof(Cx<float>) > smem_optin - 2048) C >>= 1;
+    return C;
+}
+
+int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int64_t nt, int64_t nfft,
+              int64_t ntr, double dt, double t0, int compute_real, int ascending, const double* window, bool inverse) {
+    P3D_REQUIRE(x && out, P3D_ERR_BAD_ARG, "null argument");
+    P3D_REQUIRE(nfft >= 2 && nfft % 2 == 0, P3D_ERR_BAD_ARG, "nfft must be even and >= 2 (got %lld)", (long long)nfft);
+    P3D_REQUIRE(nt >= 1 && nt <= nfft, P3D_ERR_BAD_ARG, "need 1 <= nt <= nfft (nt=%lld nfft=%lld)", (long long)nt, (long long)nfft);
+    P3D_REQUIRE(ntr >= 1, P3D_ERR_BAD_ARG, "n_traces must be >= 1");
+    P3D_REQUIRE(dt != 0.0, P3D_ERR_BAD_ARG, "dt must be non-zero");
+    int ndev = 0; P3D_CUDA(cudaGetDeviceCount(&ndev));
+    P3D_REQUIRE(device >= 0 && device < ndev, P3D_ERR_BAD_ARG, "device %d out of range", device);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop; P3D_CUDA(cudaGetDeviceProperties(&prop, device));
+
+    AxisPlan ax;
+    struct Cleanup { AxisPlan* a; void* p[3]; ~Cleanup() { a->release(); for (void* q : p) if (q) cudaFree(q); } } cl{&ax, {nullptr, nullptr, nullptr}};
+    ax.build((int)nfft);
+    const int C = choose_cols(ax.L, prop.sharedMemPerBlockOptin);
+    const size_t smem = (size_t)2 * ax.L * C * sizeof(Cx<float>);
+    P3D_REQUIRE(smem <= prop.sharedMemPerBlockOptin, P3D_ERR_NOT_IMPLEMENTED, "time axis of %lld samples does not fit in shared memory", (long long)nfft);
+
+    const int64_t nf = compute_real ? nfft / 2 + 1 : nfft;
+    // phase table in double: forward dt*exp(-2 pi i f t0)*window ; inverse exp(+2 pi i f t0)/(dt*nfft)
+    const int64_t nbins = inverse ? (compute_real ? nfft / 2 + 1 : nfft) : nf;
+    std::vector<Cx<float>> ph((size_t)nbins);
+    for (int64_t k = 0; k < nbins; ++k) {
+        const int64_t ks = (!compute_real && k >= nfft / 2) ? k - nfft : k;     // fftfreq: bin nfft/2 is -Nyquist
+        const double f = (double)ks / ((double)nfft * dt);
+        double cyc = f * t0; cyc -= std::floor(cyc);
+        const double ang = 2.0 * M_PI * cyc;
+        double amp = inverse ? 1.0 / (dt * (double)nfft) : dt;
+        if (!inverse && window) amp *= window[k];
+        ph[k] = inverse ? cmake<float>((float)(amp * cos(ang)), (float)(amp * sin(ang)))
+                        : cmake<float>((float)(amp * cos(ang)), (float)(-amp * sin(ang)));
+    }
+    Cx<float>* d_ph = nullptr;
+    P3D_CUDA(cudaMalloc(&d_ph, sizeof(Cx<float>) * nbins)); cl.p[0] = d_ph;
+    P3D_CUDA(cudaMemcpy(d_ph, ph.data(), sizeof(Cx<float>) * nbins, cudaMemcpyHostToDevice));
+
+    const size_t in_bytes = inverse ? sizeof(Cx<float>) * nf * ntr : sizeof(float) * nt * ntr;
+    const size_t out_bytes = inverse ? sizeof(float) * nt * ntr : sizeof(Cx<float>) * nf * ntr;
+    const void* din = x; void* dout = out;
+    if (x_mem == P3D_MEM_HOST) { void* p = nullptr; P3D_CUDA(cudaMalloc(&p, in_bytes)); cl.p[1] = p; P3D_CUDA(cudaMemcpy(p, x, in_bytes, cudaMemcpyHostToDevice)); din = p; }
+    if (out_mem == P3D_MEM_HOST) { void* p = nullptr; P3D_CUDA(cudaMalloc(&p, out_bytes)); cl.p[2] = p; dout = p; }
+
+    TimeGeom G; G.nt = nt; G.nf = nf; G.ntr = ntr; G.nfft = (int)nfft; G.C = C; G.compute_real = compute_real; G.ascending = ascending;
+    const long long tiles = (ntr + 2 * C - 1) / (2 * C);
+    P3D_REQUIRE(tiles < 2147483647LL, P3D_ERR_BAD_ARG, "too many traces");
+    const int threads = 512;
+    if (!inverse) {
+        P3D_CUDA(cudaFuncSetAttribute(k_time_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_time_fwd<<<(unsigned)tiles, threads, smem>>>(G, ax.dev(), (const float*)din, (Cx<float>*)dout, d_ph);
+    } else {
+        P3D_CUDA(cudaFuncSetAttribute(k_time_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_time_inv<<<(unsigned)tiles, threads, smem>>>(G, ax.dev(), (const Cx<float>*)din, (float*)dout, d_ph);
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaDeviceSynchronize());
+    if (out_mem == P3D_MEM_HOST) P3D_CUDA(cudaMemcpy(out, dout, out_bytes, cudaMemcpyDeviceToHost));
+    return P3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int p3d_time_fft(int device, const float* x, int x_mem, void* out, int out_mem, int64_t nt, int64_t nfft,
+                 int64_t n_traces, double dt, double t0, int compute_real, const double* window) {
+    try { return time_impl(device, x, x_mem, out, out_mem, nt, nfft, n_traces, dt, t0, compute_real, 0, window, false); }
+    catch (const P3dFail& f) { return f.code; }
+}
+
+int p3d_time_ifft(int device, const void* x, int x_mem, float* out, int out_mem, int64_t nfft, int64_t nt_out,
+                  int64_t n_traces, double dt, double t0, int compute_real, int ascending) {
+    try { return time_impl(device, x, x_mem, out, out_mem, nt_out, nfft, n_traces, dt, t0, compute_real, ascending, nullptr, true); }
+    catch (const P3dFail& f) { return f.code; }
+}
+
+}  // extern "C"

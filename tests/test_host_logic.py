@@ -1,0 +1,117 @@
+"""CPU-only checks: host-side mirrors against the reference's golden vectors, parameter
+translation, band sharding, the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pseudo_3d_interpolation_b200 as p3d
+from pseudo_3d_interpolation_b200 import _lib, pocs, timeaxis, synth
+from oracle.golden_cases import CASES, SCHEDULES, make_input
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "p3d_b200.h")).read()
+    declared = set(re.findall(r"\b(p3d_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"p3d_plan"}
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.p3d_abi_version() == 1
+
+
+def test_params_struct_layout_matches_header():
+    # 4 int32, 5 double, 4 int32 -> 16 + 40 + 16 = 72 bytes
+    assert ctypes.sizeof(_lib.PocsParams) == 72
+    p = pocs.make_params(niter=7, thresh_op="garrote", thresh_model="exponential-2", eps=1e-6, alpha=0.7,
+                         p_max=0.9, p_min="adaptive", sqrt_decay=True)
+    assert (p.niter, p.thresh_op, p.thresh_model, p.q, p.p_min_adaptive, p.sqrt_decay) == (7, 2, 1, 2.0, 1, 1)
+    assert pocs.make_params(thresh_model="inverse-proportional-3").q == 3.0
+    with pytest.raises(NotImplementedError):
+        pocs.make_params(thresh_model="cubic")
+    with pytest.raises(NotImplementedError):
+        pocs.make_params(thresh_op="hard-percentile")
+    with pytest.raises(ValueError):
+        pocs.make_params(decay_kind="nope")
+    with pytest.raises(TypeError):
+        pocs.make_params(p_min="1e-5")
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _lib.load().p3d_device_count() > 0:
+        pytest.skip("GPU present")
+    x = np.ones((8, 8), dtype=np.complex64)
+    with pytest.raises(_lib.P3dError):
+        p3d.POCS(x, np.ones((8, 8), np.uint8), None, transform=np.fft.fft2, itransform=np.fft.ifft2, transform_kind="FFT")
+    with pytest.raises(_lib.P3dError):
+        p3d.pocs_cube(x[None], np.ones((8, 8), np.uint8))
+    with pytest.raises(_lib.P3dError):
+        timeaxis.time_fft(np.zeros((8, 2, 2), np.float32), np.arange(8.0))
+
+
+@pytest.mark.parametrize("i", range(len(SCHEDULES)))
+def test_get_threshold_decay_matches_reference(i, golden):
+    sp = SCHEDULES[i]
+    x, _ = make_input(CASES[0])
+    X0 = np.fft.fft2(x.astype(np.complex128))
+    tau = pocs.get_threshold_decay(sp["thresh_model"], sp["niter"], "FFT", sp["p_max"], sp["p_min"], x_fwd=X0, kind=sp["kind"])
+    assert np.array_equal(tau, golden[f"schedule_{i}"])
+
+
+@pytest.mark.parametrize("kind", ["hard", "soft", "garrote"])
+@pytest.mark.parametrize("tname,tau", [("pos", 1.0 + 0.25j), ("neg", 1.0 - 0.25j), ("real", 0.8)])
+def test_threshold_matches_reference(kind, tname, tau, golden):
+    got = pocs.threshold(golden["thr_X"], tau, sub=0, kind=kind)
+    assert np.array_equal(got, golden[f"thr_{kind}_{tname}"], equal_nan=True)
+
+
+def test_threshold_errors():
+    with pytest.raises(ValueError):
+        pocs.get_threshold_decay("linear", 5, "FFT", x_fwd=None)
+    with pytest.raises(ValueError):
+        pocs.get_threshold_decay("linear", 5, "NOPE", x_fwd=np.ones(3, complex))
+    with pytest.raises(ValueError):
+        pocs.get_threshold_decay("linear", 5, "FFT", x_fwd=np.ones(3, complex), kind="bad")
+
+
+def test_band_bounds_cover_and_are_contiguous():
+    for n in (0, 1, 7, 1025, 2049):
+        for parts in (1, 2, 4, 8):
+            b = pocs.band_bounds(n, parts)
+            assert len(b) == parts and b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(parts - 1))
+            assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b if hi > lo or n == 0) <= -(-n // parts)
+
+
+def test_mask_from_fold_bit_exact():
+    fold = np.array([[0, 1, 2, 7], [255, 0, 1, 3]], dtype=np.uint8)
+    m = p3d.mask_from_fold(fold)
+    assert m.dtype == np.uint8 and np.array_equal(m, [[0, 1, 1, 1], [1, 0, 1, 1]])
+
+
+def test_synth_time_and_freq_agree():
+    """Analytic frequency slices equal the step-12 transform of the sampled time cube."""
+    from oracle import time_axis_oracle as tor
+    rng = np.random.default_rng(9)
+    nt, n1, n2 = 256, 6, 5
+    ev = synth.draw_events(rng, nt, n1, n2)
+    d, twt = synth.time_cube(ev, nt, n1, n2)
+    F, f = tor.time_fft(d, twt, compute_real=True)
+    ids = [5, 17, 40]
+    A = synth.freq_slices(ev, f[ids], n1, n2)
+    err = np.linalg.norm(A - F[ids]) / np.linalg.norm(F[ids])
+    assert err < 1e-3, err
+
+
+def test_freq_filter_window_matches_oracle():
+    from oracle import time_axis_oracle as tor
+    f = np.fft.rfftfreq(512, 0.05)
+    for ftype, freqs in (("lowpass", [3.0, 5.0]), ("highpass", [0.5, 1.5]), ("bandpass", [0.5, 1.5, 4.0, 6.0])):
+        np.testing.assert_array_equal(timeaxis.freq_filter_window(list(freqs), f, ftype), tor.freq_filter_window(list(freqs), f, ftype))
+        np.testing.assert_array_equal(timeaxis.freq_filter_keep(f, freqs, ftype), tor.freq_filter_keep(f, freqs, ftype))
