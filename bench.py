@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the FFT-POCS hot path (BASELINE.json metric: POCS slice-iterations / s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 2] [--slices S]
+
+One "step" = the POCS of S frequency slices (all iterations) of the synthetic config-2 cube
+(1000 x 1000 slices, 80 % of the traces missing, hard threshold, exponential schedule,
+100 iterations, alpha = 1, eps = 0) on every GPU; N > 1 runs one process per GPU under torchrun,
+each rank owning its own contiguous band of S slices (weak scaling, no data-path collective).
+
+Output: ONE JSON line on rank 0 (see the keys at the end of main()).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_ALG_PER_ELEM = 73.0          # 4 streaming passes x 16 B + 8 B observed data + 1 B mask
+KERNEL_BYTES_PER_ELEM = {"cols_iter": 32.0, "rows_iter": 41.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--slices", type=int, default=0, help="slices per GPU per step (0 = config default)")
+    ap.add_argument("--niter", type=int, default=0)
+    ap.add_argument("--band", type=int, default=-1, help="band_slices override (-1 = plan default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-diag", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from pseudo_3d_interpolation_b200 import synth
+    c = dict(synth.CONFIGS[args.config])
+    nf_full = c["nt"] // 2 + 1
+    default_slices = {1: 257, 2: 1025, 3: 256, 4: 64, 5: 513 * 8}[args.config]
+    ns = args.slices if args.slices > 0 else default_slices
+    niter = args.niter if args.niter > 0 else c["niter"]
+    return c, ns, niter, nf_full
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic slices generated on the device (torch is plumbing here: memory + RNG + trig)
+# ---------------------------------------------------------------------------------------------------
+def synth_device(torch, dev, cfg_id, c, first, count, nf_full):
+    from pseudo_3d_interpolation_b200 import synth
+    ev, fold, rng, _ = synth.config_case(cfg_id)
+    n1, n2 = c["n_il"], c["n_xl"]
+    f_all = np.fft.rfftfreq(c["nt"], synth.DT_MS)
+    ids = (first + np.arange(count)) % nf_full
+    ids = np.where(ids == 0, 1, ids)                      # skip the (empty) DC slice
+    f = torch.tensor(f_all[ids], dtype=torch.float64, device=dev)
+    il = torch.arange(n1, dtype=torch.float64, device=dev) - (n1 - 1) / 2.0
+    xl = torch.arange(n2, dtype=torch.float64, device=dev) - (n2 - 1) / 2.0
+    mask = torch.tensor((fold > 0).astype(np.uint8), device=dev)
+    out = torch.empty((count, n1, n2), dtype=torch.complex64, device=dev)
+    step = max(1, int(2e8 // (n1 * n2)))
+    for s0 in range(0, count, step):
+        fs = f[s0:s0 + step]
+        acc = torch.zeros((fs.numel(), n1, n2), dtype=torch.complex64, device=dev)
+        for k in range(len(ev.amp)):
+            rk = (2.0 / np.sqrt(np.pi)) * fs * fs / ev.fpk[k] ** 3 * torch.exp(-(fs / ev.fpk[k]) ** 2)
+            # separable phase: exp(-2 pi i f (t0 + tau)) * exp(-2 pi i f p il) * exp(-2 pi i f q xl)
+            ph0 = -2.0 * np.pi * fs * (synth.T0_MS + ev.tau[k])
+            a0 = (ev.amp[k] * rk) * torch.exp(1j * torch.remainder(ph0, 2 * np.pi))
+            a1 = torch.exp(-2j * np.pi * fs[:, None] * (ev.p[k] * il)[None, :])
+            a2 = torch.exp(-2j * np.pi * fs[:, None] * (ev.q[k] * xl)[None, :])
+            acc += ((a0[:, None] * a1)[:, :, None] * a2[:, None, :]).to(torch.complex64)
+        out[s0:s0 + step] = acc * mask[None]
+    return out, mask
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for nme, val in zip(names, p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle (port of the reference algorithm) over a bounded sample of slices
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    import numpy as _np
+    from oracle import pocs_oracle as orc
+    x, mask, params = job
+    t0 = time.perf_counter()
+    info = {}
+    orc.pocs_slice(x, mask, info=info, **params)
+    return info["niterations"], time.perf_counter() - t0
+
+
+def cpu_sample(cfg_id, c, niter, n_slices, procs):
+    """Time `n_slices` slices (complex64 input, as the real pipeline feeds numpy >= 2) on `procs` processes."""
+    from pseudo_3d_interpolation_b200 import synth
+    ids = list(range(8, 8 + n_slices))
+    d, fold, _ = synth.sparse_freq_slices(cfg_id, ids)
+    mask = np.minimum(fold, 1).astype(np.uint8)
+    params = dict(niter=niter, thresh_op=c["thresh_op"], thresh_model=c["thresh_model"], eps=0.0, alpha=c["alpha"], p_max=0.99, p_min=1e-5)
+    jobs = [(d[i], mask, params) for i in range(n_slices)]
+    t0 = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs, chunksize=1)
+    else:
+        res = [_cpu_worker(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    its = sum(r[0] for r in res)
+    return its / wall, wall, its
+
+
+def cpu_niter_for_budget(c, procs, budget_s=20.0):
+    # ~135 ms per 1000x1000 iteration per core, scaled by size
+    per_it = 135e-3 * (c["n_il"] * c["n_xl"]) / 1e6
+    return max(4, int(budget_s / per_it))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    c, ns, niter, nf_full = workload(args)
+    n1, n2 = c["n_il"], c["n_xl"]
+    cfg_workload = (f"C{args.config}: {n1}x{n2} iline x xline slices of the {c['nt']}-sample cube, "
+                    f"{'line-pattern' if c['keep'] == 'lines' else str(int(round((1 - c['keep']) * 100))) + '%'} traces missing, "
+                    f"FFT-POCS {c['thresh_op']} threshold, {c['thresh_model']} schedule, {niter} iterations, alpha={c['alpha']}, eps=0; "
+                    f"{ns} rfft slices per GPU per step")
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        procs = min(os.cpu_count() or 1, 64)
+        it_cpu = min(niter, cpu_niter_for_budget(c, procs, 12.0))
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, wall, its = cpu_sample(args.config, c, it_cpu, procs, procs)
+            if i >= args.warmup:
+                vals.append((v, wall))
+        value = float(np.mean([v for v, _ in vals]))
+        ms = float(np.mean([w for _, w in vals]) * 1e3)
+        sample = f"{procs} slices x {it_cpu} iterations per step, one slice per process ({procs} processes), complex64 input"
+        line = {"impl": "reference", "metric": "pocs_slice_iterations_per_s", "value": value, "unit": "slice-iterations/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+                "config": {"workload": cfg_workload, "inputs": "host numpy arrays"},
+                "cpu_baseline": {"value": value, "unit": "slice-iterations/s", "cores": procs, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "slice-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import pseudo_3d_interpolation_b200 as p3d
+    from pseudo_3d_interpolation_b200 import _lib
+
+    _lib.require_gpu()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    params = p3d.make_params(niter=niter, thresh_op=c["thresh_op"], thresh_model=c["thresh_model"], eps=0.0, alpha=c["alpha"],
+                             p_max=0.99, p_min=1e-5)
+    x_dev, mask_dev = synth_device(torch, dev, args.config, c, rank * ns, ns, nf_full)
+    out_dev = torch.empty_like(x_dev)
+    torch.cuda.synchronize()
+    plan = p3d.PocsPlan(n1, n2, device=local)
+    if args.band >= 0:
+        plan.set_option("band_slices", args.band)
+    desc = plan.describe()
+    nit = np.zeros(ns, np.int32)
+
+    def step_device():
+        plan.run_device(x_dev.data_ptr(), mask_dev.data_ptr(), out_dev.data_ptr(), ns, params, nit=nit)
+
+    for _ in range(args.warmup):
+        step_device()
+    gpu_index = local
+    if os.environ.get("CUDA_VISIBLE_DEVICES"):
+        try:
+            gpu_index = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+        except Exception:
+            gpu_index = local
+    sampler = ClockSampler(gpu_index)
+    plan.set_profiling(True)
+    plan.get_profile(reset=True)
+    barrier()
+    sampler.start()
+    plan.event_record(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+    plan.event_record(1)
+    dev_ms = plan.event_elapsed_ms(0, 1)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    prof = plan.get_profile(reset=True)
+    plan.set_profiling(False)
+    slice_its = int(nit.sum())                          # per step, this rank
+    assert slice_its == ns * niter, (slice_its, ns * niter)
+
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    tot_its = torch.tensor([float(slice_its)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_its, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    total_its_per_step = float(tot_its[0])
+    value = total_its_per_step * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- end to end: pinned host buffers in, pinned host buffers out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hx = _lib.PinnedArray((ns, n1, n2), np.complex64)
+        ho = _lib.PinnedArray((ns, n1, n2), np.complex64)
+        hm = _lib.PinnedArray((n1, n2), np.uint8)
+        _lib.check(_lib.load().p3d_memcpy(local, _lib.ptr(hx.array), x_dev.data_ptr(), hx.nbytes, 1))
+        _lib.check(_lib.load().p3d_memcpy(local, _lib.ptr(hm.array), mask_dev.data_ptr(), hm.nbytes, 1))
+        del x_dev, out_dev
+        torch.cuda.empty_cache()
+
+        def step_e2e():
+            plan.run(hx.array, hm.array, out=ho.array, params=params)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        plan.event_record(2)
+        for _ in range(args.steps):
+            step_e2e()
+        plan.event_record(3)
+        e_ms = plan.event_elapsed_ms(2, 3)
+        barrier()
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_its_per_step * args.steps / (float(te[0]) * 1e-3), "unit": "slice-iterations/s",
+               "h2d_bytes_per_step": int(hx.nbytes + hm.nbytes), "d2h_bytes_per_step": int(ho.nbytes + ns * (niter + 2) * 8),
+               "ms_per_step": float(te[0]) / args.steps, "api": "PocsPlan.run -> p3d_pocs_run(host pinned in/out)"}
+        checksum = float(np.abs(ho.array[0]).sum())
+    else:
+        checksum = float(out_dev[0].abs().sum())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (CUDA events around every launch, on the launch stream)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max(KERNEL_BYTES_PER_ELEM, key=lambda k: prof[k]["ms"])
+    launches = prof[dom]["launches"]
+    avg_ms = prof[dom]["ms"] / max(launches, 1)
+    slices_per_launch = ns * args.steps * niter / max(launches, 1)
+    alg_bytes = KERNEL_BYTES_PER_ELEM[dom] * n1 * n2 * slices_per_launch
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+                "whole_iteration": {"alg_bytes_per_slice_iteration": B_ALG_PER_ELEM * n1 * n2,
+                                    "achieved_GBps": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9,
+                                    "frac_of_measured_peak": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9 / peak,
+                                    "frac_of_8TBps_nominal": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9 / 8000.0},
+                "kernel_share_of_step": {k: prof[k]["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())) for k in prof if prof[k]["launches"]}}
+    gpu_launches = int(sum(v["launches"] for v in prof.values()))
+
+    # ---- diagnostic: cuFFT + elementwise chain (torch.fft) on the same device, same slice shape
+    diag = None
+    if not args.no_diag:
+        try:
+            nb = min(16, ns)
+            xs = torch.randn((nb, n1, n2), dtype=torch.complex64, device=dev)
+            msk = (torch.rand((n1, n2), device=dev) < 0.2).to(torch.float32)
+            d0 = xs * msk
+            xx = d0.clone()
+            keep = (1.0 - msk)
+            def chain(nit_):
+                nonlocal xx
+                for k in range(nit_):
+                    X = torch.fft.fft2(xx)
+                    X = torch.where(X.abs() < 10.0 + k, torch.zeros_like(X), X)
+                    y = torch.fft.ifft2(X)
+                    xx = y * keep + d0
+                    _ = xx.abs().sum()
+            chain(3)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); chain(10); e1.record(); torch.cuda.synchronize()
+            diag = {"what": "torch.fft.fft2/ifft2 (cuFFT) + torch elementwise chain, hard threshold, same shape",
+                    "value": nb * 10 / (e0.elapsed_time(e1) * 1e-3), "unit": "slice-iterations/s", "slices": nb}
+        except Exception as ex:          # noqa: BLE001
+            diag = {"error": str(ex)[:200]}
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        procs = min(os.cpu_count() or 1, 64)
+        it_cpu = min(niter, cpu_niter_for_budget(c, procs, 15.0))
+        v, wall, its = cpu_sample(args.config, c, it_cpu, procs, procs)
+        cpu = {"value": v, "unit": "slice-iterations/s", "cores": procs, "kind": "port",
+               "sample": f"{procs} slices x {it_cpu} iterations, one slice per process ({procs} processes), complex64 input, {wall:.1f} s"}
+
+    line = {"metric": "pocs_slice_iterations_per_s", "value": value, "unit": "slice-iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c64 (fp32 complex)", "data": "synthetic",
+            "config": {"workload": cfg_workload, "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2" % (ns * n1 * n2 * 8 / 1e9),
+                       "plan": desc, "timing": "CUDA events on the library stream, max over ranks",
+                       "wall_ms_per_step": wall_ms_max / args.steps},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+            "diag_cufft_chain": diag, "checksum": checksum}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

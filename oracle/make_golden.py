@@ -43,6 +43,11 @@ def main():
         store[f"{n}__y"] = np.asarray(y)
         store[f"{n}__niterations"] = np.int64(info["niterations"])
         store[f"{n}__costs"] = costs
+        # the reference's OWN complex64 path (what numpy >= 2 runs in production) against its
+        # float64 result: the fp32 conditioning floor of this case
+        if not case.get("all_zero"):
+            y32 = fn(x, mask, None, transform=np.fft.fft2, itransform=np.fft.ifft2, transform_kind="FFT", **case["params"])
+            store[f"{n}__c64_drift"] = np.float64(np.linalg.norm(y32 - y) / np.linalg.norm(y))
         print(f"{n:28s} shape={x.shape} niterations={info['niterations']:3d} cost={float(info['cost']):.3e}")
 
     # schedule tables on the spectrum of case 0

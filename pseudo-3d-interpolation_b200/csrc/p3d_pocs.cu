@@ -155,9 +155,9 @@ void choose_geometry(p3d_plan* P) {
     P->geom.slices_per_mask = 1;
     P->col_smem = (size_t)2 * L1 * C * sizeof(Cx<float>);
     P->row_smem = (size_t)2 * pitch2 * RB * sizeof(Cx<float>);
-    auto pick_threads = [](long work) { return work >= 8192 ? 512 : (work >= 2048 ? 256 : 128); };
-    P->col_threads = pick_threads((long)L1 * C / 4);
-    P->row_threads = pick_threads((long)L2 * RB / 4);
+    auto pick_threads = [](long elems) { long t = ((elems / 8 + 31) / 32) * 32; return (int)std::min<long>(512, std::max<long>(128, t)); };
+    P->col_threads = pick_threads((long)L1 * C);
+    P->row_threads = pick_threads((long)L2 * RB);
 }
 
 GenericCfg generic_cfg(p3d_plan* P) {
@@ -695,6 +695,7 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     if (!strcmp(key, "band_slices")) P->band_slices = (int)value;
     else if (!strcmp(key, "force_generic")) P->force_generic = value != 0;
     else if (!strcmp(key, "lanes")) P->n_lanes = (int)value;
+    else if (!strcmp(key, "spec_variant")) P->spec = select_spec_kernels(P->n1, P->n2, (int)value);
     else if (!strcmp(key, "max_slices")) { P->max_slices = value; for (auto& L : P->lanes) { cudaStream_t st = L.stream; L.stream = nullptr; free_lane(L); L.stream = st; } }
     else { set_error("unknown option %s", key); return P3D_ERR_BAD_ARG; }
     return P3D_OK;

@@ -14,6 +14,6 @@ struct SpecKernels {
     const char* rows_name = "generic";
 };
 
-SpecKernels select_spec_kernels(int n_iline, int n_xline);
+SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant = 0);
 
 }  // namespace p3d

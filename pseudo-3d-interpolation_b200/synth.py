@@ -91,12 +91,17 @@ def freq_slices(ev: Events, freqs, n_il, n_xl, t0=T0_MS, dtype=np.complex64):
     """Analytic step-12 output for the listed frequencies -> (len(freqs), n_il, n_xl)."""
     freqs = np.asarray(freqs, dtype=np.float64)
     out = np.zeros((freqs.size, n_il, n_xl), dtype=np.complex128)
-    delays = _delays(ev, n_il, n_xl, t0)
+    il = np.arange(n_il, dtype=np.float64) - (n_il - 1) / 2.0
+    xl = np.arange(n_xl, dtype=np.float64) - (n_xl - 1) / 2.0
     for i, f in enumerate(freqs):
         acc = np.zeros((n_il, n_xl), dtype=np.complex128)
-        for k, delay in enumerate(delays):
+        for k in range(len(ev.amp)):
             rk = (2.0 / np.sqrt(np.pi)) * f * f / ev.fpk[k] ** 3 * np.exp(-(f / ev.fpk[k]) ** 2)
-            acc += ev.amp[k] * rk * np.exp(-2j * np.pi * f * delay)
+            # the plane-wave phase is separable in (il, xl): one outer product per event
+            a0 = ev.amp[k] * rk * np.exp(-2j * np.pi * f * (t0 + ev.tau[k]))
+            a1 = np.exp(-2j * np.pi * f * ev.p[k] * il)
+            a2 = np.exp(-2j * np.pi * f * ev.q[k] * xl)
+            acc += np.outer(a0 * a1, a2)
         out[i] = acc
     return out.astype(dtype)
 

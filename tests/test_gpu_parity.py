@@ -44,7 +44,12 @@ def test_pocs_matches_reference_golden(case, golden, p3d):
     else:
         assert info["niterations"] == nit_ref
     if info["niterations"] == nit_ref:
-        assert rel_l2(y, ref) <= RTOL, rel_l2(y, ref)
+        # Tolerance 1e-4, except where the reference's own complex64 path already drifts more
+        # than that from its float64 result (hard threshold sinking into the noise floor,
+        # SURVEY 8a-C): there the bound is 3x that measured floor.
+        floor = float(golden[f"{n}__c64_drift"]) if f"{n}__c64_drift" in golden else 0.0
+        tol = RTOL if floor <= 0.3 * RTOL else 3.0 * floor
+        assert rel_l2(y, ref) <= tol, (rel_l2(y, ref), floor)
     if case["params"]["alpha"] == 1.0 and not case.get("all_zero"):
         obs = mask == 1
         assert np.array_equal(np.asarray(y)[obs], x[obs])     # observed traces reproduced exactly
@@ -112,6 +117,64 @@ def test_cube_matches_oracle_config1_shrunk(p3d):
     obs = orc.mask_from_fold(fold) == 1
     assert np.array_equal(y[:, obs], d[:, obs])
     assert np.all(res["niterations"] == 25)
+
+
+@pytest.mark.parametrize("shape,op,model,niter,alpha", [
+    ((256, 256), "hard", "exponential", 12, 1.0),
+    ((256, 256), "soft", "linear", 10, 0.7),
+    ((256, 256), "garrote", "exponential", 10, 1.0),
+    ((200, 200), "hard", "exponential", 12, 1.0),
+    ((1000, 1000), "hard", "exponential", 8, 1.0),
+    ((1000, 256), "garrote", "linear", 6, 1.0),
+    ((256, 1000), "soft", "exponential", 6, 0.7),
+    ((2000, 200), "hard", "exponential", 5, 1.0),
+    ((200, 2000), "hard", "linear", 5, 1.0),
+])
+def test_specialised_kernels_match_oracle(shape, op, model, niter, alpha, p3d):
+    """shapes served by the register-resident kernels (p3d_pocs_spec.cu), vs the float64 oracle
+    and vs the generic kernels of the same library."""
+    case = dict(seed=77, shape=shape, keep=0.3, nwaves=5)
+    x, mask = make_input(case)
+    params = dict(niter=niter, thresh_op=op, thresh_model=model, eps=0.0, alpha=alpha, p_max=0.99, p_min=1e-4)
+    plan = p3d.PocsPlan(*shape)
+    assert "spec<" in plan.describe()
+    y, info = plan.run(x, mask, **params)
+    ref = orc.pocs_slice(x.astype(np.complex128), mask, **params)
+    assert rel_l2(y[0], ref) <= RTOL, rel_l2(y[0], ref)
+    if alpha == 1.0:
+        assert np.array_equal(y[0][mask == 1], x[mask == 1])
+    plan.set_option("force_generic", 1)
+    yg, _ = plan.run(x, mask, **params)
+    assert rel_l2(y[0], yg[0]) <= 2e-5
+    if shape == (1000, 1000):
+        plan.set_option("force_generic", 0)
+        plan.set_option("spec_variant", 1)
+        y1, _ = plan.run(x, mask, **params)
+        assert rel_l2(y1[0], ref) <= RTOL
+
+
+def test_early_exit_many_slices(p3d):
+    """per-slice early exit (device-side stop flags) on a spec shape: iteration counts match the oracle."""
+    xs, refs, nits = [], [], []
+    params = dict(niter=60, thresh_op="hard", thresh_model="exponential", eps=1e-9, alpha=1.0, p_max=0.99, p_min=1e-5)
+    mask = None
+    for sd in range(5):
+        x, m = make_input(dict(seed=11, shape=(256, 256), keep=0.35, nwaves=3 + sd))
+        mask = m
+        xs.append(x * (1.0 + sd))
+    x = np.stack(xs)
+    x[2] = 0                                         # an all-zero slice in the middle
+    for i in range(x.shape[0]):
+        info = {}
+        refs.append(orc.pocs_slice(x[i].astype(np.complex128), mask, info=info, **params))
+        nits.append(info["niterations"])
+    plan = p3d.PocsPlan(256, 256)
+    y, info = plan.run(x, mask, **params)
+    assert info["niterations"][2] == 0 and np.array_equal(y[2], x[2])
+    for i in range(x.shape[0]):
+        assert abs(int(info["niterations"][i]) - nits[i]) <= 1, (i, info["niterations"][i], nits[i])
+        if int(info["niterations"][i]) == nits[i]:
+            assert rel_l2(y[i], refs[i]) <= RTOL
 
 
 def test_per_cube_masks(p3d):
