@@ -39,8 +39,7 @@ std::vector<int> factorize_radices(int n) {
         }
         if (!found) return {};
     }
-    if (r.empty()) r.push_back(1);
-    return r;
+    return r;          // n == 1: no pass at all
 }
 
 int bluestein_length(int n) {
@@ -100,7 +99,7 @@ void AxisPlan::build(int n_) {
     bluestein = !is_smooth(n);
     L = bluestein ? bluestein_length(n) : n;
     radix = factorize_radices(L);
-    P3D_REQUIRE(!radix.empty() && (int)radix.size() <= P3D_MAX_PASSES, P3D_ERR_NOT_IMPLEMENTED,
+    P3D_REQUIRE((L == 1 || !radix.empty()) && (int)radix.size() <= P3D_MAX_PASSES, P3D_ERR_NOT_IMPLEMENTED,
                 "cannot factorise transform length %d", L);
     std::vector<Cx<float>> tw((size_t)L);
     for (int t = 0; t < L; ++t) {

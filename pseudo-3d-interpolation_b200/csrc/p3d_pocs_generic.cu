@@ -41,8 +41,15 @@ template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t generic_configure(const GenericCfg& c) {
+cudaError_t generic_configure(const GenericCfg& cfg) {
+    // The attribute is per kernel, not per plan: always raise it to the device's opt-in maximum
+    // so that plans with different tile sizes can coexist in one process.
+    int dev = 0, optin = 0;
     cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    struct { size_t col_smem, row_smem; } c = {(size_t)optin, (size_t)optin};
+    if (cfg.col_smem > (size_t)optin || cfg.row_smem > (size_t)optin) return cudaErrorInvalidValue;
 #define P3D_SET(k, b) if ((e = set_smem(k, b)) != cudaSuccess) return e
     P3D_SET((k_cols_generic<float, 0, 0>), c.col_smem);
     P3D_SET((k_cols_generic<float, 1, P3D_OP_HARD>), c.col_smem);

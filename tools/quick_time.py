@@ -35,6 +35,8 @@ def main():
     plan = p3d.PocsPlan(n1, n2, band_slices=band)
     if force_generic:
         plan.set_option("force_generic", 1)
+    if len(a) > 7:
+        plan.set_option("spec_variant", int(a[7]))
     print(plan.describe())
     dx = _lib.DeviceBuffer(x.nbytes); dx.upload(x)
     dm = _lib.DeviceBuffer(mask.nbytes); dm.upload(mask)
