@@ -127,10 +127,11 @@ def threshold_table(X0, niter, thresh_model="exponential", p_max=0.99, p_min=1e-
 def apply_threshold(X, tau, kind="hard"):
     """Threshold operator with the reference's complex-``tau`` semantics."""
     X = np.asarray(X)
-    # keep a real tau real: numpy then uses real division (a / r) where a complex tau uses
-    # complex division -- they round differently
-    tau = complex(tau) if np.iscomplexobj(tau) else float(tau)
-    a, b = (tau.real, tau.imag) if isinstance(tau, complex) else (tau, 0.0)
+    # ``tau`` is used as the numpy scalar it is in the reference (an element of the schedule
+    # array): numpy >= 2 treats numpy scalars as strongly typed, so a complex128 tau promotes a
+    # complex64 spectrum to complex128 in the soft / garrote branches exactly as the reference
+    # does, and a real tau uses real division (a / r) where a complex tau uses complex division.
+    a, b = np.real(tau), np.imag(tau)
     r = np.abs(X)
     if kind == "hard":
         kill = (r < a) | ((r == a) & (0.0 < b))
@@ -179,11 +180,19 @@ def pocs_slice(x, mask, niter=50, thresh_op="hard", thresh_model="exponential", 
     X0 = np.fft.fft2(x)
     tau = threshold_table(X0, niter, thresh_model, p_max, p_min, decay_kind)
     keep = 1 - alpha * mask
+    v_fast = 1
     x_prev = x
     k_done = 0
     for k in range(niter):
-        if version in ("regular", "fast"):       # 'fast' == 'regular' 
+        if version == "regular":
             x_in = x_prev
+        elif version == "fast":
+            # x_old aliases x_inv in the reference (functions/POCS.py:629), so the momentum term
+            # is frac * 0; kept literally because frac (float64) promotes the dtype
+            v1 = (1 + np.sqrt(1 + 4 * v_fast ** 2)) / 2
+            frac = (v_fast - 1) / (v1 + 1)
+            v_fast = v1
+            x_in = x_prev + frac * (x_prev - x_prev)
         elif version == "adaptive":
             x_tmp = alpha * x + keep * x_prev
             x_in = x_tmp + (1 - alpha) * (x - mask * x_prev)
@@ -193,7 +202,11 @@ def pocs_slice(x, mask, niter=50, thresh_op="hard", thresh_model="exponential", 
         t = np.sqrt(tau[k]) if sqrt_decay else tau[k]
         Y = apply_threshold(X, t, thresh_op)
         y = np.fft.ifft2(Y)
-        x_new = y * keep + x * alpha
+        # in place, like the reference (functions/POCS.py:616-619): a complex64 iterate stays
+        # complex64 under numpy >= 2 (the production path), a complex128 one stays complex128
+        y *= keep
+        y += x * alpha
+        x_new = y
         # cost: reference sums (|x_k| - |x_{k-1}|) element-wise first (functions/POCS.py:622)
         cost = np.sum(np.abs(x_new) - np.abs(x_prev)) ** 2 / np.sum(np.abs(x_new)) ** 2
         costs.append(float(cost))

@@ -8,36 +8,65 @@
 //   * an inverse transform can be followed by an element-wise step and a forward transform
 //     without leaving registers (the fusion the POCS iteration kernels are built on).
 // Each pass: per-thread Q = E/R radix-R butterflies (every radix must divide E).
+//
+// Exchanges alternate between two shared-memory buffers, so each exchange needs a single
+// __syncthreads(): the writes of exchange i+1 go to the buffer nobody reads any more, and the
+// writes of exchange i+2 are ordered after the reads of exchange i by the barrier of i+1.
+//
+// Exchange layout.  After the pass with (Ns, R) the Stockham output position is
+//   pos = hi*(Ns*R) + r*Ns + k        (butterfly b = hi*Ns + k, output r)
+// and it is stored at  pos + hi*DELTA : every block of B = Ns*R positions is followed by DELTA
+// padding elements.  DELTA is chosen per exchange so that the 16 lanes of a half-warp (8-byte
+// accesses) fall into distinct banks for the writes (stride B+DELTA odd for Ns = 1; block
+// starts continuing the run of k for Ns > 1), while the reads stay (almost) consecutive.
+// Because T is a multiple of B or B a multiple of T, both the write and the read address
+// split into a per-thread base plus a compile-time offset: no per-access index arithmetic.
 #pragma once
 #include "p3d_butterflies.cuh"
 
 namespace p3d {
 
-// Smem accessor concept:  Cx<T>& at(int pos)  -- maps a line position to this thread's line storage.
+__host__ __device__ constexpr int exch_delta(int Ns, int R) {
+    const int B = Ns * R;
+    if (Ns == 1) return (R % 2 == 0) ? 1 : 0;
+    int d = (Ns - B) % 16;
+    if (d < 0) d += 16;
+    return d;
+}
+// storage needed per line (elements), upper bound over all exchanges
+__host__ __device__ constexpr int padded_line(int N) { return N + N / 6 + 16; }
 
-template <int N, int E, int DIR, int Ns, typename T, typename Acc, int... Rs> struct RegPasses;
+// Accessor concept:
+//   static constexpr int STRIDE;            element stride of consecutive line positions
+//   Cx<T>* line(int buf) const;             this thread's line in buffer 0/1
 
-template <int N, int E, int DIR, int Ns, typename T, typename Acc>
-struct RegPasses<N, E, DIR, Ns, T, Acc> {
+template <int N, int E, int DIR, int Ns, int BUF, typename T, typename Acc, int... Rs> struct RegPasses;
+
+template <int N, int E, int DIR, int Ns, int BUF, typename T, typename Acc>
+struct RegPasses<N, E, DIR, Ns, BUF, T, Acc> {
     static_assert(Ns == N, "radix sequence does not multiply to N");
     __device__ __forceinline__ static void run(Cx<T> (&)[E], const Acc&, const int, const Cx<T>* __restrict__) {}
 };
 
-template <int N, int E, int DIR, int Ns, typename T, typename Acc, int R, int... Rest>
-struct RegPasses<N, E, DIR, Ns, T, Acc, R, Rest...> {
+template <int N, int E, int DIR, int Ns, int BUF, typename T, typename Acc, int R, int... Rest>
+struct RegPasses<N, E, DIR, Ns, BUF, T, Acc, R, Rest...> {
     static constexpr int TT = N / E;          // threads per line
     static constexpr int Q = E / R;           // butterflies per thread in this pass
+    static constexpr int B = Ns * R;          // Stockham block of this pass
+    static constexpr int DELTA = exch_delta(Ns, R);
     static_assert(E % R == 0, "every radix must divide the elements per thread");
     static_assert(N % (Ns * R) == 0, "radix sequence does not multiply to N");
 
     __device__ __forceinline__ static void run(Cx<T> (&v)[E], const Acc& acc, const int j, const Cx<T>* __restrict__ tw) {
         constexpr bool last = (sizeof...(Rest) == 0);
-        int kk[Q];
+        constexpr int S = Acc::STRIDE;
+        int wbase[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int b = j + q * TT;
-            const int k = (Ns == 1) ? 0 : (b % Ns);
-            kk[q] = k;
+            const int hi = (Ns == 1) ? b : (b / Ns);
+            const int k = (Ns == 1) ? 0 : (b - hi * Ns);
+            wbase[q] = hi * (B + DELTA) + k;
             Cx<T> x[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) x[r] = v[q + r * Q];
@@ -54,18 +83,27 @@ struct RegPasses<N, E, DIR, Ns, T, Acc, R, Rest...> {
             for (int r = 0; r < R; ++r) v[q + r * Q] = x[r];
         }
         if constexpr (!last) {
+            static_assert(TT % B == 0 || B % TT == 0, "threads per line and Stockham block must nest");
+            Cx<T>* line = acc.line(BUF);
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const int b = j + q * TT;
-                const int j0 = (b - kk[q]) * R + kk[q];
+                Cx<T>* w = line + wbase[q] * S;
 #pragma unroll
-                for (int r = 0; r < R; ++r) acc.at(j0 + r * Ns) = v[q + r * Q];
+                for (int r = 0; r < R; ++r) w[(r * Ns) * S] = v[q + r * Q];
             }
             __syncthreads();
+            if constexpr (TT % B == 0) {
+                // hi(pos) = j/B + e*(TT/B)
+                const Cx<T>* rd = line + (j + DELTA * (j / B)) * S;
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = acc.at(j + e * TT);
-            __syncthreads();
-            RegPasses<N, E, DIR, Ns * R, T, Acc, Rest...>::run(v, acc, j, tw);
+                for (int e = 0; e < E; ++e) v[e] = rd[(e * (TT + DELTA * (TT / B))) * S];
+            } else {
+                // hi(pos) = e / (B/TT)
+                const Cx<T>* rd = line + j * S;
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = rd[(e * TT + DELTA * (e / (B / TT))) * S];
+            }
+            RegPasses<N, E, DIR, Ns * R, BUF ^ 1, T, Acc, Rest...>::run(v, acc, j, tw);
         }
     }
 };
@@ -75,9 +113,12 @@ template <int N_, int E_, int... Rs> struct LinePlan {
     static constexpr int N = N_;
     static constexpr int E = E_;
     static constexpr int T = N_ / E_;
-    template <int DIR, typename TT, typename Acc>
+    static constexpr int NEXCH = (int)sizeof...(Rs) - 1;      // shared-memory exchanges per transform
+    static constexpr int LINE = padded_line(N_);              // storage per line and buffer (elements)
+    // BUF0: buffer used by the first exchange; the next transform should start with (BUF0 + NEXCH) & 1
+    template <int DIR, int BUF0, typename TT, typename Acc>
     __device__ __forceinline__ static void fft(Cx<TT> (&v)[E_], const Acc& acc, const int j, const Cx<TT>* __restrict__ tw) {
-        RegPasses<N_, E_, DIR, 1, TT, Acc, Rs...>::run(v, acc, j, tw);
+        RegPasses<N_, E_, DIR, 1, BUF0, TT, Acc, Rs...>::run(v, acc, j, tw);
     }
 };
 

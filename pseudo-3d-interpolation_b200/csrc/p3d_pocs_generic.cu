@@ -48,8 +48,9 @@ cudaError_t generic_configure(const GenericCfg& cfg) {
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-    struct { size_t col_smem, row_smem; } c = {(size_t)optin, (size_t)optin};
-    if (cfg.col_smem > (size_t)optin || cfg.row_smem > (size_t)optin) return cudaErrorInvalidValue;
+    // (kernels with a little static shared memory need headroom below the opt-in limit)
+    struct { size_t col_smem, row_smem; } c = {(size_t)optin - 1024, (size_t)optin - 1024};
+    if (cfg.col_smem > c.col_smem || cfg.row_smem > c.row_smem) return cudaErrorInvalidValue;
 #define P3D_SET(k, b) if ((e = set_smem(k, b)) != cudaSuccess) return e
     P3D_SET((k_cols_generic<float, 0, 0>), c.col_smem);
     P3D_SET((k_cols_generic<float, 1, P3D_OP_HARD>), c.col_smem);

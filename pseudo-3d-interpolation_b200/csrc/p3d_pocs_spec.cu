@@ -12,25 +12,17 @@
 namespace p3d {
 
 // ---- shared-memory accessors ---------------------------------------------------------------------
-// column tile: [pos][c], c fastest.  For C = 8 two consecutive positions share a 128-byte
-// bank row; the gray-code swizzle keeps every access pattern of the Stockham passes
-// (consecutive positions, stride-R positions) conflict free.
-template <int C> struct ColAcc {
+// Two buffers (see p3d_fft_reg.cuh).  Column tile: [addr][c], c fastest; row tile: [row][addr].
+template <int C, int LINE> struct ColAcc {
+    static constexpr int STRIDE = C;
     Cx<float>* base;   // already offset by c
-    __device__ __forceinline__ Cx<float>& at(int pos) const {
-        if (C == 8) {
-            const int g = (pos ^ (pos >> 1)) & 1;
-            return base[((pos >> 1) << 4) + (g << 3)];
-        }
-        return base[pos * C];
-    }
+    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (LINE * C); }
 };
-// row tile: [row][pos + pad], one padding element every 32 positions
-struct RowAcc {
+template <int RB, int LINE> struct RowAcc {
+    static constexpr int STRIDE = 1;
     Cx<float>* base;   // already offset by the row
-    __device__ __forceinline__ Cx<float>& at(int pos) const { return base[pos + (pos >> 5)]; }
+    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (RB * LINE); }
 };
-__host__ __device__ constexpr int row_pitch(int n) { return n + (n >> 5) + 1; }
 
 // ---- column kernel ---------------------------------------------------------------------------------
 template <typename LP, int C, int MINB>
@@ -44,14 +36,14 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     const int c = tid % C, j = tid / C;
     const int col = blockIdx.x * C + c;
     const bool ok = col < G.n2;
-    Cx<float>* Ws = A.W + (long long)s * N * G.n2 + col;
-    ColAcc<C> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    Cx<float>* __restrict__ Ws = A.W + (long long)s * N * G.n2 + col;
+    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
 
     Cx<float> v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(j + e * T) * G.n2] : cmake<float>(0.f, 0.f);
 
-    LP::template fft<-1, float>(v, acc, j, tw);
+    LP::template fft<-1, 0, float>(v, acc, j, tw);
 
     const Cx<float> tau = A.tau[(long long)s * A.niter + A.k];
     const float a = tau.x, b = tau.y;
@@ -67,7 +59,7 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
         for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_GARROTE, float>(v[e], a, b, t2re, t2im);
     }
 
-    LP::template fft<+1, float>(v, acc, j, tw);
+    LP::template fft<+1, (LP::NEXCH & 1), float>(v, acc, j, tw);
 
     if (ok) {
 #pragma unroll
@@ -82,6 +74,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_s[32];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
+    static_assert(E <= 32, "mask bits are packed into one register");
     const int s = blockIdx.y;
     if (A.stop[s] != 0) return;
     const int tid = threadIdx.x;
@@ -90,28 +83,39 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     const bool ok = row < G.n1;
     const long long off = (long long)s * G.n1 * N + (long long)row * N + j;
     const long long moff = ((A.first_slice + s) / G.slices_per_mask) * (long long)G.n1 * N + (long long)row * N + j;
-    RowAcc acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * row_pitch(N);
+    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    Cx<float>* __restrict__ Wp = A.W + off;
+    const Cx<float>* __restrict__ Dp = A.D + off;
+    const uint8_t* __restrict__ Mp = A.mask + moff;
+    Cx<float>* __restrict__ Op = A.OUT + off;
 
     Cx<float> v[E];
+    unsigned mbits = 0u;
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = ok ? A.W[off + e * T] : cmake<float>(0.f, 0.f);
+    for (int e = 0; e < E; ++e) v[e] = ok ? Wp[e * T] : cmake<float>(0.f, 0.f);
+    // the mask bytes ride along with the first batch of loads (one register across the transform)
+#pragma unroll
+    for (int e = 0; e < E; ++e) mbits |= (ok && Mp[e * T] != 0) ? (1u << e) : 0u;
 
-    LP::template fft<+1, float>(v, acc, j, tw);
+    LP::template fft<+1, 0, float>(v, acc, j, tw);
 
     float part = 0.f;
     if (ok) {
+        // all observed-data loads are issued before the first use (one exposed latency, not E)
+        Cx<float> d[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) d[e] = Dp[e * T];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const Cx<float> d = A.D[off + e * T];
-            const float m = (float)A.mask[moff + e * T];
+            const float m = ((mbits >> e) & 1u) ? 1.f : 0.f;
             const float coef = (1.f - A.alpha * m) * A.inv_n;
-            Cx<float> x = cmake<float>(fmaf(coef, v[e].x, A.alpha * d.x), fmaf(coef, v[e].y, A.alpha * d.y));
+            Cx<float> x = cmake<float>(fmaf(coef, v[e].x, A.alpha * d[e].x), fmaf(coef, v[e].y, A.alpha * d[e].y));
             part += sqrtf(x.x * x.x + x.y * x.y);
-            if (A.write_out) A.OUT[off + e * T] = x;
+            if (A.write_out) Op[e * T] = x;
             if (A.adaptive) {
                 const float keep = 1.f - A.alpha * m, om = 1.f - A.alpha;
-                const Cx<float> xt = cmake<float>(A.alpha * d.x + keep * x.x, A.alpha * d.y + keep * x.y);
-                x = cmake<float>(xt.x + om * (d.x - m * x.x), xt.y + om * (d.y - m * x.y));
+                const Cx<float> xt = cmake<float>(A.alpha * d[e].x + keep * x.x, A.alpha * d[e].y + keep * x.y);
+                x = cmake<float>(xt.x + om * (d[e].x - m * x.x), xt.y + om * (d[e].y - m * x.y));
             }
             v[e] = x;
         }
@@ -127,18 +131,18 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     }
     if (A.last) return;
 
-    LP::template fft<-1, float>(v, acc, j, tw);
+    LP::template fft<-1, (LP::NEXCH & 1), float>(v, acc, j, tw);
 
     if (ok) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) A.W[off + e * T] = v[e];
+        for (int e = 0; e < E; ++e) Wp[e * T] = v[e];
     }
 }
 
 // ---- registry ----------------------------------------------------------------------------------------
 template <typename LP, int C, int MINB>
 static void launch_cols(const PocsGeom& G, const AxisDev<float>& ax, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
-    constexpr size_t smem = (size_t)LP::N * C * sizeof(Cx<float>);
+    constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<float>);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_cols_spec<LP, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -149,7 +153,7 @@ static void launch_cols(const PocsGeom& G, const AxisDev<float>& ax, const BandA
 }
 template <typename LP, int RB, int MINB>
 static void launch_rows(const PocsGeom& G, const AxisDev<float>& ax, const BandArgs<float>& A, int ns, cudaStream_t st) {
-    constexpr size_t smem = (size_t)row_pitch(LP::N) * RB * sizeof(Cx<float>);
+    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_rows_spec<LP, RB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -193,10 +193,10 @@ int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int6
     P3D_REQUIRE(tiles < 2147483647LL, P3D_ERR_BAD_ARG, "too many traces");
     const int threads = 512;
     if (!inverse) {
-        P3D_CUDA(cudaFuncSetAttribute(k_time_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        P3D_CUDA(cudaFuncSetAttribute(k_time_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
         k_time_fwd<<<(unsigned)tiles, threads, smem>>>(G, ax.dev(), (const float*)din, (Cx<float>*)dout, d_ph);
     } else {
-        P3D_CUDA(cudaFuncSetAttribute(k_time_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        P3D_CUDA(cudaFuncSetAttribute(k_time_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
         k_time_inv<<<(unsigned)tiles, threads, smem>>>(G, ax.dev(), (const Cx<float>*)din, (float*)dout, d_ph);
     }
     P3D_CUDA(cudaGetLastError());

@@ -16,6 +16,7 @@ for ver in ("adaptive", "regular"):
             for niter in (2, 3, 5, 20):
                 params = dict(niter=niter, thresh_op=op, thresh_model="exponential", eps=0.0, alpha=alpha, p_max=0.99, p_min=1e-4)
                 ref = orc.pocs_slice(x.astype(np.complex128), mask, version=ver, **params)
-                plan = p3d.get_plan(*x.shape)
+                plan = p3d.pocs.get_plan(*x.shape)
                 y, _ = plan.run(x, mask, version=ver, **params)
-                print(f"{ver:9s} {op:5s} alpha={alpha} niter={niter:2d}: {rel(y[0], ref):.3e}")
+                other = orc.pocs_slice(x.astype(np.complex128), mask, version=("regular" if ver == "adaptive" else "adaptive"), **params)
+                print(f"{ver:9s} {op:5s} alpha={alpha} niter={niter:2d}: vs-same-version {rel(y[0], ref):.3e}   vs-other-version {rel(y[0], other):.3e}")
