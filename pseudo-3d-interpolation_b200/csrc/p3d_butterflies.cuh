@@ -162,11 +162,39 @@ template <int R1, int R2, int DIR, typename T> struct BflyCT {
         }
     }
 };
-template <int DIR, typename T> struct Bfly<6, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<2, 3, DIR, T>::run(v); } };
+// composite radix R = R1 * R2 with gcd(R1, R2) = 1: Good-Thomas prime-factor mapping, NO twiddles.
+//   input  n = (R2 n1 + R1 n2) mod R,   output k with k = k1 (mod R1), k = k2 (mod R2)
+//   X[k] = sum_{n2} W_R2^{n2 k2} sum_{n1} x[n] W_R1^{n1 k1}
+__host__ __device__ constexpr int pfa_out_index(int R1, int R2, int k1, int k2) {
+    for (int k = 0; k < R1 * R2; ++k) if (k % R1 == k1 && k % R2 == k2) return k;
+    return -1;
+}
+template <int R1, int R2, int DIR, typename T> struct BflyPFA {
+    __device__ __forceinline__ static void run(Cx<T>* v) {
+        constexpr int R = R1 * R2;
+        Cx<T> y[R2][R1];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) y[n2][n1] = v[(R2 * n1 + R1 * n2) % R];
+            Bfly<R1, DIR, T>::run(y[n2]);
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            Cx<T> z[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) z[n2] = y[n2][k1];
+            Bfly<R2, DIR, T>::run(z);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) v[pfa_out_index(R1, R2, k1, k2)] = z[k2];
+        }
+    }
+};
+template <int DIR, typename T> struct Bfly<6, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<2, 3, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<8, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<2, 4, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<9, DIR, T>  { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<3, 3, DIR, T>::run(v); } };
-template <int DIR, typename T> struct Bfly<10, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<2, 5, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<10, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<2, 5, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<16, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<4, 4, DIR, T>::run(v); } };
-template <int DIR, typename T> struct Bfly<20, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<4, 5, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<20, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<4, 5, DIR, T>::run(v); } };
 
 }  // namespace p3d

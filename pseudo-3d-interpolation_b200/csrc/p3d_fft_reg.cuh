@@ -40,16 +40,20 @@ __host__ __device__ constexpr int padded_line(int N) { return N + N / 6 + 16; }
 //   static constexpr int STRIDE;            element stride of consecutive line positions
 //   Cx<T>* line(int buf) const;             this thread's line in buffer 0/1
 
-template <int N, int E, int DIR, int Ns, int BUF, typename T, typename Acc, int... Rs> struct RegPasses;
+// Twiddles: one table per twiddled pass, laid out [k][R] (k = b mod Ns < Ns, entry r = W^{r k},
+// W = exp(-2 pi i / (Ns R)); entry 0 is 1 and unused) so that a butterfly reads its R-1 factors
+// as R/2 consecutive 16-byte loads from ONE computed address.  Tables of consecutive passes are
+// concatenated (offset TWOFF).  Host side: spec_twiddle_table().
+template <int N, int E, int DIR, int Ns, int BUF, int TWOFF, typename T, typename Acc, int... Rs> struct RegPasses;
 
-template <int N, int E, int DIR, int Ns, int BUF, typename T, typename Acc>
-struct RegPasses<N, E, DIR, Ns, BUF, T, Acc> {
+template <int N, int E, int DIR, int Ns, int BUF, int TWOFF, typename T, typename Acc>
+struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc> {
     static_assert(Ns == N, "radix sequence does not multiply to N");
     __device__ __forceinline__ static void run(Cx<T> (&)[E], const Acc&, const int, const Cx<T>* __restrict__) {}
 };
 
-template <int N, int E, int DIR, int Ns, int BUF, typename T, typename Acc, int R, int... Rest>
-struct RegPasses<N, E, DIR, Ns, BUF, T, Acc, R, Rest...> {
+template <int N, int E, int DIR, int Ns, int BUF, int TWOFF, typename T, typename Acc, int R, int... Rest>
+struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
     static constexpr int TT = N / E;          // threads per line
     static constexpr int Q = E / R;           // butterflies per thread in this pass
     static constexpr int B = Ns * R;          // Stockham block of this pass
@@ -71,11 +75,21 @@ struct RegPasses<N, E, DIR, Ns, BUF, T, Acc, R, Rest...> {
 #pragma unroll
             for (int r = 0; r < R; ++r) x[r] = v[q + r * Q];
             if (Ns > 1) {
-                const int t1 = k * (N / (Ns * R));
+                const Cx<T>* trow = tw + TWOFF + k * R;
+                if constexpr (R % 2 == 0 && sizeof(T) == 4) {
+                    const float4* t4 = reinterpret_cast<const float4*>(trow);
 #pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    const Cx<T> w = tw[r * t1];
-                    x[r] = (DIR < 0) ? cmul(x[r], w) : cmulc(x[r], w);
+                    for (int r2 = 0; r2 < R / 2; ++r2) {
+                        const float4 w = __ldg(t4 + r2);
+                        if (r2 > 0) x[2 * r2] = (DIR < 0) ? cmul(x[2 * r2], cmake<T>(w.x, w.y)) : cmulc(x[2 * r2], cmake<T>(w.x, w.y));
+                        x[2 * r2 + 1] = (DIR < 0) ? cmul(x[2 * r2 + 1], cmake<T>(w.z, w.w)) : cmulc(x[2 * r2 + 1], cmake<T>(w.z, w.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 1; r < R; ++r) {
+                        const Cx<T> w = trow[r];
+                        x[r] = (DIR < 0) ? cmul(x[r], w) : cmulc(x[r], w);
+                    }
                 }
             }
             Bfly<R, DIR, T>::run(x);
@@ -103,7 +117,7 @@ struct RegPasses<N, E, DIR, Ns, BUF, T, Acc, R, Rest...> {
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = rd[(e * TT + DELTA * (e / (B / TT))) * S];
             }
-            RegPasses<N, E, DIR, Ns * R, BUF ^ 1, T, Acc, Rest...>::run(v, acc, j, tw);
+            RegPasses<N, E, DIR, Ns * R, BUF ^ 1, TWOFF + (Ns > 1 ? Ns * R : 0), T, Acc, Rest...>::run(v, acc, j, tw);
         }
     }
 };
@@ -115,10 +129,12 @@ template <int N_, int E_, int... Rs> struct LinePlan {
     static constexpr int T = N_ / E_;
     static constexpr int NEXCH = (int)sizeof...(Rs) - 1;      // shared-memory exchanges per transform
     static constexpr int LINE = padded_line(N_);              // storage per line and buffer (elements)
+    static constexpr int NPASS = (int)sizeof...(Rs);
+    static void radices(int* out) { const int r[] = {Rs...}; for (int i = 0; i < NPASS; ++i) out[i] = r[i]; }
     // BUF0: buffer used by the first exchange; the next transform should start with (BUF0 + NEXCH) & 1
     template <int DIR, int BUF0, typename TT, typename Acc>
     __device__ __forceinline__ static void fft(Cx<TT> (&v)[E_], const Acc& acc, const int j, const Cx<TT>* __restrict__ tw) {
-        RegPasses<N_, E_, DIR, 1, BUF0, TT, Acc, Rs...>::run(v, acc, j, tw);
+        RegPasses<N_, E_, DIR, 1, BUF0, 0, TT, Acc, Rs...>::run(v, acc, j, tw);
     }
 };
 

@@ -53,6 +53,9 @@ struct p3d_plan {
     int n_lanes = 0;                 // 0 = auto
     std::vector<Lane> lanes;
     uint8_t* d_mask = nullptr; int64_t d_mask_bytes = 0;
+    uint32_t* d_mbits = nullptr; int64_t d_mbits_words = 0;    // packed mask of the specialised row kernel
+    Cx<float>* spec_tw_cols = nullptr;                          // per-pass twiddle tables (p3d_fft_reg.cuh)
+    Cx<float>* spec_tw_rows = nullptr;
     void* cub_temp = nullptr; size_t cub_temp_bytes = 0;
     cudaEvent_t ev[8] = {nullptr};
     // profiling
@@ -166,6 +169,21 @@ GenericCfg generic_cfg(p3d_plan* P) {
     return c;
 }
 
+// (re)select the specialised kernels and upload their per-pass twiddle tables
+void install_spec(p3d_plan* P, int variant) {
+    P->spec = select_spec_kernels(P->n1, P->n2, variant);
+    auto upload = [](const std::vector<int>& radices, Cx<float>** dst) {
+        if (*dst) { cudaFree(*dst); *dst = nullptr; }
+        if (radices.empty()) return;
+        std::vector<Cx<float>> t = spec_twiddle_table(radices);
+        P3D_CUDA(cudaMalloc(dst, sizeof(Cx<float>) * t.size()));
+        P3D_CUDA(cudaMemcpy(*dst, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    };
+    upload(P->spec.cols_radices, &P->spec_tw_cols);
+    upload(P->spec.rows_radices, &P->spec_tw_rows);
+    P->d_mbits_words = 0;           // layout may have changed: repack on the next run
+}
+
 // ---- launches -----------------------------------------------------------------------------------
 void launch_rows_init(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices) {
     prof_begin(P, st, 0);
@@ -181,14 +199,14 @@ void launch_cols_stats(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, i
 }
 void launch_cols_iter(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices, int op) {
     prof_begin(P, st, 2);
-    if (P->spec.cols_iter && !P->force_generic) P->spec.cols_iter(P->geom, P->ax1.dev(), A, nslices, op, st);
+    if (P->spec.cols_iter && !P->force_generic) P->spec.cols_iter(P->geom, P->spec_tw_cols, A, nslices, op, st);
     else generic_cols_iter(generic_cfg(P), P->ax1.dev(), A, nslices, op, st);
     prof_end(P, st);
     P3D_CUDA(cudaGetLastError());
 }
 void launch_rows_iter(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices) {
     prof_begin(P, st, 3);
-    if (P->spec.rows_iter && !P->force_generic) P->spec.rows_iter(P->geom, P->ax2.dev(), A, nslices, st);
+    if (P->spec.rows_iter && !P->force_generic) P->spec.rows_iter(P->geom, P->spec_tw_rows, A, nslices, st);
     else generic_rows_iter(generic_cfg(P), P->ax2.dev(), A, nslices, st);
     prof_end(P, st);
     P3D_CUDA(cudaGetLastError());
@@ -287,6 +305,22 @@ void ensure_mask(p3d_plan* P, const uint8_t* mask, int64_t bytes, int mem, cudaS
     *dmask = P->d_mask;
 }
 
+// packed mask words for the specialised row kernel (rebuilt every run: the mask may have changed)
+const uint32_t* pack_mask(p3d_plan* P, const uint8_t* dmask, int64_t n_masks, cudaStream_t st) {
+    if (!P->spec.pack_mask) return nullptr;
+    const int64_t words = n_masks * (int64_t)P->n1 * P->spec.rows_T;
+    if (words > P->d_mbits_words || !P->d_mbits) {
+        if (P->d_mbits) cudaFree(P->d_mbits);
+        P->d_mbits = nullptr; P->d_mbits_words = 0;
+        P3D_CUDA(cudaMalloc(&P->d_mbits, sizeof(uint32_t) * words));
+        P->d_mbits_words = words;
+    }
+    P->spec.pack_mask(dmask, P->d_mbits, (int)n_masks, P->n1, st);
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaStreamSynchronize(st));
+    return P->d_mbits;
+}
+
 int64_t auto_capacity(p3d_plan* P, int64_t n_slices, int nbuf_per_lane, int lanes) {
     size_t free_b = 0, total_b = 0;
     P3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -299,7 +333,7 @@ int64_t auto_capacity(p3d_plan* P, int64_t n_slices, int nbuf_per_lane, int lane
 
 struct RunCtx {
     p3d_plan* P; const p3d_pocs_params* pr;
-    const Cx<float>* x; int x_mem; const uint8_t* dmask; int64_t spm;
+    const Cx<float>* x; int x_mem; const uint8_t* dmask; const uint32_t* dmbits; int64_t spm;
     Cx<float>* out; int out_mem;
     int32_t* niter_out; double* cost_out; double* costs_out;
     double* tau_out;            // schedule-only mode
@@ -361,7 +395,7 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
 
     BandArgs<float> A;
     memset(&A, 0, sizeof(A));
-    A.mask = R.dmask; A.niter = niter; A.eps = pr.eps; A.alpha = (float)pr.alpha;
+    A.mask = R.dmask; A.mbits = R.dmbits; A.niter = niter; A.eps = pr.eps; A.alpha = (float)pr.alpha;
     A.inv_n = (float)(1.0 / ((double)P->n1 * (double)P->n2));
     const bool data_driven = pr.thresh_model == P3D_MODEL_DATA_DRIVEN;
     const bool adaptive = pr.version == P3D_VERSION_ADAPTIVE;
@@ -528,10 +562,11 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     R.P = P; R.pr = pr; R.x = (const Cx<float>*)x; R.x_mem = x_mem; R.spm = spm;
     R.out = (Cx<float>*)out; R.out_mem = out_mem; R.niter_out = niter_out; R.cost_out = cost_out;
     R.costs_out = costs_out; R.tau_out = tau_out; R.schedule_only = schedule_only;
-    R.dmask = nullptr;
+    R.dmask = nullptr; R.dmbits = nullptr;
     if (!schedule_only) {
         const int64_t n_masks = (n_slices + spm - 1) / spm;
         ensure_mask(P, mask, n_masks * (int64_t)P->n1 * P->n2, x_mem, P->lanes[0].stream, &R.dmask);
+        R.dmbits = pack_mask(P, R.dmask, n_masks, P->lanes[0].stream);
     }
 
     int li = 0;
@@ -580,7 +615,7 @@ int p3d_plan_create(p3d_plan** plan, int device, int n_iline, int n_xline, int64
         P->ax2.build(n_xline);
         choose_geometry(P);
         { cudaError_t ce = generic_configure(generic_cfg(P)); P3D_CUDA(ce); }
-        P->spec = select_spec_kernels(n_iline, n_xline);
+        install_spec(P, 0);
     } catch (...) { p3d_plan_destroy(P); throw; }
     *plan = P;
     return P3D_OK;
@@ -593,6 +628,9 @@ int p3d_plan_destroy(p3d_plan* P) {
     for (auto& L : P->lanes) { free_lane(L); if (L.stream) cudaStreamDestroy(L.stream); }
     P->ax1.release(); P->ax2.release();
     if (P->d_mask) cudaFree(P->d_mask);
+    if (P->d_mbits) cudaFree(P->d_mbits);
+    if (P->spec_tw_cols) cudaFree(P->spec_tw_cols);
+    if (P->spec_tw_rows) cudaFree(P->spec_tw_rows);
     if (P->cub_temp) cudaFree(P->cub_temp);
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
     delete P;
@@ -695,7 +733,9 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     if (!strcmp(key, "band_slices")) P->band_slices = (int)value;
     else if (!strcmp(key, "force_generic")) P->force_generic = value != 0;
     else if (!strcmp(key, "lanes")) P->n_lanes = (int)value;
-    else if (!strcmp(key, "spec_variant")) P->spec = select_spec_kernels(P->n1, P->n2, (int)value);
+    else if (!strcmp(key, "spec_variant")) {
+        try { DeviceGuard g(P->device); install_spec(P, (int)value); } catch (const P3dFail& f) { return f.code; }
+    }
     else if (!strcmp(key, "max_slices")) { P->max_slices = value; for (auto& L : P->lanes) { cudaStream_t st = L.stream; L.stream = nullptr; free_lane(L); L.stream = st; } }
     else { set_error("unknown option %s", key); return P3D_ERR_BAD_ARG; }
     return P3D_OK;

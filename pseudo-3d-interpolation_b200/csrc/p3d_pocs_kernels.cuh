@@ -55,6 +55,7 @@ template <typename T> struct BandArgs {
     const Cx<T>* D;              // observed slices
     Cx<T>* OUT;                  // result slices (also scratch for X0 in the data-driven setup)
     const uint8_t* mask;         // [n_masks][n1][n2]
+    const uint32_t* mbits;       // [n_masks][n1][T] packed mask words of the specialised row kernel (or null)
     long long first_slice;       // global index of the band's first slice (for the mask lookup)
     const Cx<T>* tau;            // [band][niter]
     double* S;                   // [band][niter+1]  (S[.][0] = sum|d|, S[.][k+1] = sum|x_k|)
@@ -69,18 +70,29 @@ template <typename T> struct BandArgs {
 // ---------------------------------------------------------------------------------------------
 // threshold operators with the reference's complex-tau semantics
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float p3d_rsqrt(float v) { return rsqrtf(v); }
+__device__ __forceinline__ double p3d_rsqrt(double v) { return 1.0 / sqrt(v); }
+
 template <int OP, typename T>
 __device__ __forceinline__ Cx<T> apply_threshold(Cx<T> X, const T a, const T b, const T t2re, const T t2im) {
     const T r2 = X.x * X.x + X.y * X.y;
     if (OP == P3D_OP_HARD) {
-        const T r = sqrt(r2);
-        const bool kill = (r < a) || (r == a && b > T(0));
+        // |X| < a  <=>  |X|^2 < a^2 for a > 0 (never true for a <= 0): no square root on the hot
+        // path.  Only when |X|^2 is within a few ulps of a^2 is the comparison redone on |X|
+        // itself, exactly as the statistics kernel formed max|X0| / min|X0| (so that the element
+        // that DEFINES a threshold is never killed by it) and with the lexicographic tie rule
+        // |X| == a  =>  kill iff Im(tau) > 0.
+        const T a2 = a * a;
+        bool kill = (a > T(0)) && (r2 < a2);
+        if (fabs(r2 - a2) <= T(2e-6) * a2) {
+            const T r = sqrt(r2);
+            kill = (r < a) || (r == a && b > T(0));
+        }
         return kill ? cmake<T>(T(0), T(0)) : X;
     } else if (OP == P3D_OP_SOFT) {
-        const T r = sqrt(r2);
-        const T inv = T(1) / r;
+        const T inv = p3d_rsqrt(r2);        // 1/|X| (inf for X == 0, handled below)
         T fre = T(1) - a * inv, fim = -(b * inv);
-        const bool zero = (r == T(0)) || (fre < T(0)) || (fre == T(0) && fim < T(0));
+        const bool zero = (r2 == T(0)) || (fre < T(0)) || (fre == T(0) && fim < T(0));
         if (zero) return cmake<T>(T(0), T(0));
         return cmake<T>(X.x * fre - X.y * fim, X.x * fim + X.y * fre);
     } else {

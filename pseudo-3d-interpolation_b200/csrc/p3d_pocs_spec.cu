@@ -9,6 +9,8 @@
 #include "p3d_pocs_spec.cuh"
 #include "p3d_fft_reg.cuh"
 
+#include <cmath>
+
 namespace p3d {
 
 // ---- shared-memory accessors ---------------------------------------------------------------------
@@ -74,7 +76,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_s[32];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
-    static_assert(E <= 32, "mask bits are packed into one register");
+    static_assert(E <= 32, "mask bits are packed into one 32-bit word");
     const int s = blockIdx.y;
     if (A.stop[s] != 0) return;
     const int tid = threadIdx.x;
@@ -82,20 +84,17 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     const int row = blockIdx.x * RB + rr;
     const bool ok = row < G.n1;
     const long long off = (long long)s * G.n1 * N + (long long)row * N + j;
-    const long long moff = ((A.first_slice + s) / G.slices_per_mask) * (long long)G.n1 * N + (long long)row * N + j;
     RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
     Cx<float>* __restrict__ Wp = A.W + off;
     const Cx<float>* __restrict__ Dp = A.D + off;
-    const uint8_t* __restrict__ Mp = A.mask + moff;
     Cx<float>* __restrict__ Op = A.OUT + off;
 
     Cx<float> v[E];
-    unsigned mbits = 0u;
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = ok ? Wp[e * T] : cmake<float>(0.f, 0.f);
-    // the mask bytes ride along with the first batch of loads (one register across the transform)
-#pragma unroll
-    for (int e = 0; e < E; ++e) mbits |= (ok && Mp[e * T] != 0) ? (1u << e) : 0u;
+    // one packed mask word per thread (bit e <-> column j + e*T) rides along with the first loads
+    const long long midx = (A.first_slice + s) / G.slices_per_mask;
+    const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
 
     LP::template fft<+1, 0, float>(v, acc, j, tw);
 
@@ -139,9 +138,23 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     }
 }
 
+// mask bytes -> one word per (mask, row, j): bit e = mask[row][j + e*T] != 0
+template <int T, int E>
+__global__ void k_pack_mask(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits, long long total_rows) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total_rows * T) return;
+    const long long row = i / T;
+    const int j = (int)(i - row * T);
+    const uint8_t* m = mask + row * (long long)(T * E) + j;
+    unsigned w = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) w |= (m[e * T] != 0) ? (1u << e) : 0u;
+    bits[i] = w;
+}
+
 // ---- registry ----------------------------------------------------------------------------------------
 template <typename LP, int C, int MINB>
-static void launch_cols(const PocsGeom& G, const AxisDev<float>& ax, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
+static void launch_cols(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
     constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<float>);
     static bool configured = false;
     if (!configured) {
@@ -149,10 +162,10 @@ static void launch_cols(const PocsGeom& G, const AxisDev<float>& ax, const BandA
         configured = true;
     }
     dim3 grid((G.n2 + C - 1) / C, ns);
-    k_cols_spec<LP, C, MINB><<<grid, LP::T * C, smem, st>>>(G, ax.tw, A, op);
+    k_cols_spec<LP, C, MINB><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
 }
 template <typename LP, int RB, int MINB>
-static void launch_rows(const PocsGeom& G, const AxisDev<float>& ax, const BandArgs<float>& A, int ns, cudaStream_t st) {
+static void launch_rows(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {
     constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
     static bool configured = false;
     if (!configured) {
@@ -160,7 +173,37 @@ static void launch_rows(const PocsGeom& G, const AxisDev<float>& ax, const BandA
         configured = true;
     }
     dim3 grid((G.n1 + RB - 1) / RB, ns);
-    k_rows_spec<LP, RB, MINB><<<grid, LP::T * RB, smem, st>>>(G, ax.tw, A);
+    k_rows_spec<LP, RB, MINB><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+}
+template <typename LP>
+static void launch_pack(const uint8_t* mask, uint32_t* bits, int n_masks, int n1, cudaStream_t st) {
+    const long long rows = (long long)n_masks * n1;
+    const long long total = rows * LP::T;
+    k_pack_mask<LP::T, LP::E><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mask, bits, rows);
+}
+
+template <typename LP> static std::vector<int> radices_of() {
+    std::vector<int> r(LP::NPASS);
+    LP::radices(r.data());
+    return r;
+}
+
+std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices) {
+    std::vector<Cx<float>> t;
+    long Ns = 1;
+    for (size_t p = 0; p < radices.size(); ++p) {
+        const int R = radices[p];
+        if (Ns > 1) {
+            for (long k = 0; k < Ns; ++k)
+                for (int r = 0; r < R; ++r) {
+                    const double ang = -2.0 * M_PI * (double)((r * k) % (Ns * R)) / (double)(Ns * R);
+                    t.push_back(cmake<float>((float)cos(ang), (float)sin(ang)));
+                }
+        }
+        Ns *= R;
+    }
+    if (t.empty()) t.push_back(cmake<float>(1.f, 0.f));
+    return t;
 }
 
 typedef LinePlan<1000, 10, 10, 10, 10> LP1000;
@@ -168,26 +211,30 @@ typedef LinePlan<2000, 10, 10, 10, 10, 2> LP2000;
 typedef LinePlan<256, 16, 16, 16> LP256;
 typedef LinePlan<200, 20, 10, 20> LP200;
 
+#define P3D_COLS(LP, C, MINB, NAME) do { k.cols_iter = launch_cols<LP, C, MINB>; k.cols_name = NAME; k.cols_radices = radices_of<LP>(); } while (0)
+#define P3D_ROWS(LP, RB, MINB, NAME) do { k.rows_iter = launch_rows<LP, RB, MINB>; k.rows_name = NAME; k.rows_radices = radices_of<LP>(); \
+                                          k.pack_mask = launch_pack<LP>; k.rows_T = LP::T; } while (0)
+
 SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
     SpecKernels k;
     switch (n_iline) {      // column transforms have the length of the iline axis
         case 1000:
-            if (variant == 1) { k.cols_iter = launch_cols<LP1000, 8, 1>; k.cols_name = "spec<1000,E10,10x10x10,C8,1cta>"; }
-            else              { k.cols_iter = launch_cols<LP1000, 4, 2>; k.cols_name = "spec<1000,E10,10x10x10,C4,2cta>"; }
+            if (variant == 1) P3D_COLS(LP1000, 8, 1, "spec<1000,E10,10x10x10,C8,1cta>");
+            else              P3D_COLS(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta>");
             break;
-        case 2000: k.cols_iter = launch_cols<LP2000, 4, 1>;  k.cols_name = "spec<2000,E10,10x10x10x2,C4>"; break;
-        case 256:  k.cols_iter = launch_cols<LP256, 16, 3>;  k.cols_name = "spec<256,E16,16x16,C16>"; break;
-        case 200:  k.cols_iter = launch_cols<LP200, 16, 4>;  k.cols_name = "spec<200,E20,10x20,C16>"; break;
+        case 2000: P3D_COLS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4>"); break;
+        case 256:  P3D_COLS(LP256, 16, 3, "spec<256,E16,16x16,C16>"); break;
+        case 200:  P3D_COLS(LP200, 16, 4, "spec<200,E20,10x20,C16>"); break;
         default: break;
     }
     switch (n_xline) {      // row transforms have the length of the xline axis
         case 1000:
-            if (variant == 1) { k.rows_iter = launch_rows<LP1000, 8, 1>; k.rows_name = "spec<1000,E10,10x10x10,RB8,1cta>"; }
-            else              { k.rows_iter = launch_rows<LP1000, 4, 2>; k.rows_name = "spec<1000,E10,10x10x10,RB4,2cta>"; }
+            if (variant == 1) P3D_ROWS(LP1000, 8, 1, "spec<1000,E10,10x10x10,RB8,1cta>");
+            else              P3D_ROWS(LP1000, 4, 2, "spec<1000,E10,10x10x10,RB4,2cta>");
             break;
-        case 2000: k.rows_iter = launch_rows<LP2000, 4, 1>;  k.rows_name = "spec<2000,E10,10x10x10x2,RB4>"; break;
-        case 256:  k.rows_iter = launch_rows<LP256, 16, 3>;  k.rows_name = "spec<256,E16,16x16,RB16>"; break;
-        case 200:  k.rows_iter = launch_rows<LP200, 16, 4>;  k.rows_name = "spec<200,E20,10x20,RB16>"; break;
+        case 2000: P3D_ROWS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,RB4>"); break;
+        case 256:  P3D_ROWS(LP256, 16, 3, "spec<256,E16,16x16,RB16>"); break;
+        case 200:  P3D_ROWS(LP200, 16, 4, "spec<200,E20,10x20,RB16>"); break;
         default: break;
     }
     return k;

@@ -1,19 +1,29 @@
 // Specialised (compile-time size, register-resident) POCS kernels.  See DESIGN.md.
 #pragma once
+#include <vector>
 #include "p3d_pocs_kernels.cuh"
 
 namespace p3d {
 
-typedef void (*ColsIterLaunch)(const PocsGeom&, const AxisDev<float>&, const BandArgs<float>&, int nslices, int op, cudaStream_t);
-typedef void (*RowsIterLaunch)(const PocsGeom&, const AxisDev<float>&, const BandArgs<float>&, int nslices, cudaStream_t);
+// tw: the per-pass twiddle tables of the line plan (spec_twiddle_table), device memory
+typedef void (*ColsIterLaunch)(const PocsGeom&, const Cx<float>* tw, const BandArgs<float>&, int nslices, int op, cudaStream_t);
+typedef void (*RowsIterLaunch)(const PocsGeom&, const Cx<float>* tw, const BandArgs<float>&, int nslices, cudaStream_t);
+// packs mask bytes into one word per (row, thread): bit e = mask[row][j + e*T]
+typedef void (*PackMaskLaunch)(const uint8_t* mask, uint32_t* bits, int n_masks, int n1, cudaStream_t);
 
 struct SpecKernels {
     ColsIterLaunch cols_iter = nullptr;
     RowsIterLaunch rows_iter = nullptr;
+    PackMaskLaunch pack_mask = nullptr;
     const char* cols_name = "generic";
     const char* rows_name = "generic";
+    std::vector<int> cols_radices, rows_radices;   // for the twiddle tables
+    int rows_T = 0;                                 // threads per row line (packed-mask layout)
 };
 
 SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant = 0);
+
+// Host: concatenated [k][R] tables of every twiddled pass (see p3d_fft_reg.cuh), computed in double.
+std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices);
 
 }  // namespace p3d
