@@ -233,26 +233,30 @@ def test_full_size_config_slices(p3d):
 
 
 def test_full_size_config_slices_soft(p3d):
-    """Same slices with the soft operator (continuous): fp32 holds 1e-4 against float64."""
+    """Same slices with the soft operator (continuous): fp32 holds 1e-4 against float64 --
+    except on slices where the reference's own choice of z = x_fwd.max() (largest REAL part,
+    SURVEY Q1) is a near tie: an fp32-sized perturbation then selects the other coefficient and
+    the whole schedule tau = p * z jumps (a discontinuity of the reference algorithm, visible in
+    the float64 oracle itself).  Such slices are identified from the float64 spectrum and only
+    bounded loosely."""
     from pseudo_3d_interpolation_b200 import synth
-    d, fold, c = synth.sparse_freq_slices(1, slice_ids=[20, 100, 200])
+    ids = [20, 60, 100, 140, 200]
+    d, fold, c = synth.sparse_freq_slices(1, slice_ids=ids)
     params = dict(niter=c["niter"], thresh_op="soft", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-5)
     y = p3d.pocs_cube(d, fold, **params)
     ref = orc.pocs_cube(d, fold, **params)
-    # Even the continuous operators inherit one discontinuity from the reference: tau = p * z with
-    # z = the element of largest REAL part of the initial spectrum (complex .max(), SURVEY Q1).
-    # When two coefficients nearly tie on the real part an fp32-sized perturbation of the input
-    # selects the other one and tau jumps.  The float64 oracle itself shows this (measured below),
-    # so the bound is max(1e-4, 3 x the oracle's own sensitivity to a 1.2e-7 input perturbation).
-    rng = np.random.default_rng(5)
-    floor = 0.0
-    for _ in range(3):
-        dp = d.astype(np.complex128)
-        scale = np.sqrt(np.mean(np.abs(dp) ** 2, axis=(1, 2), keepdims=True)) / np.sqrt(np.mean(dp != 0))
-        dp = dp + 1.2e-7 * scale * (rng.standard_normal(dp.shape) + 1j * rng.standard_normal(dp.shape)) * (dp != 0)
-        floor = max(floor, rel_l2(orc.pocs_cube(dp, fold, **params), ref))
-    print(f"soft full size: gpu {rel_l2(y, ref):.3e}, float64-oracle sensitivity {floor:.3e}")
-    assert rel_l2(y, ref) <= max(RTOL, 3.0 * floor), (rel_l2(y, ref), floor)
+    n_strict = 0
+    for i in range(len(ids)):
+        re = np.sort(np.fft.fft2(d[i].astype(np.complex128)).real.ravel())
+        gap = (re[-1] - re[-2]) / abs(re[-1])
+        err = rel_l2(y[i], ref[i])
+        print(f"slice {ids[i]}: rel-L2 {err:.3e}, relative gap of the two largest real parts {gap:.2e}")
+        if gap > 1e-5:
+            n_strict += 1
+            assert err <= RTOL, (ids[i], err, gap)
+        else:
+            assert err <= 5e-3, (ids[i], err, gap)
+    assert n_strict >= 2
 
 
 def test_per_cube_masks(p3d):
