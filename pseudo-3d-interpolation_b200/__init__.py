@@ -10,6 +10,6 @@ Public surface (mirrors the reference for the one accelerated path):
 """
 from . import _lib                                   # noqa: F401
 from .pocs import (POCS_algorithm, POCS, FPOCS, APOCS, get_threshold_decay, threshold, pocs_cube,  # noqa: F401
-                   PocsPlan, make_params, mask_from_fold, fft2, ifft2, band_bounds)
+                   PocsPlan, make_params, mask_from_fold, fft2, ifft2, band_bounds, set_default_precision)
 
 __version__ = "0.1.0"

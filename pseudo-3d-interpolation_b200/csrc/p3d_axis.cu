@@ -131,12 +131,55 @@ void AxisPlan::build(int n_) {
     }
 }
 
+void AxisPlan::build64() {
+    if (d_tw64) return;
+    std::vector<Cx<double>> tw((size_t)L);
+    for (int t = 0; t < L; ++t) {
+        const double ang = -2.0 * M_PI * (double)t / (double)L;
+        tw[t] = cmake<double>(cos(ang), sin(ang));
+    }
+    P3D_CUDA(cudaMalloc(&d_tw64, sizeof(Cx<double>) * L));
+    P3D_CUDA(cudaMemcpy(d_tw64, tw.data(), sizeof(Cx<double>) * L, cudaMemcpyHostToDevice));
+    if (bluestein) {
+        std::vector<std::complex<double>> w((size_t)n);
+        for (int j = 0; j < n; ++j) {
+            const long j2 = ((long)j * j) % (2L * n);
+            const double ang = -M_PI * (double)j2 / (double)n;
+            w[j] = std::complex<double>(cos(ang), sin(ang));
+        }
+        std::vector<std::complex<double>> b((size_t)L, 0.0);
+        for (int j = 0; j < n; ++j) { b[j] = std::conj(w[j]); if (j > 0) b[L - j] = std::conj(w[j]); }
+        host_fft(b, false);
+        std::vector<Cx<double>> ch((size_t)n), bf((size_t)L);
+        for (int j = 0; j < n; ++j) ch[j] = cmake<double>(w[j].real(), w[j].imag());
+        for (int j = 0; j < L; ++j) bf[j] = cmake<double>(b[j].real() / L, b[j].imag() / L);
+        P3D_CUDA(cudaMalloc(&d_chirp64, sizeof(Cx<double>) * n));
+        P3D_CUDA(cudaMemcpy(d_chirp64, ch.data(), sizeof(Cx<double>) * n, cudaMemcpyHostToDevice));
+        P3D_CUDA(cudaMalloc(&d_bfilt64, sizeof(Cx<double>) * L));
+        P3D_CUDA(cudaMemcpy(d_bfilt64, bf.data(), sizeof(Cx<double>) * L, cudaMemcpyHostToDevice));
+    }
+}
+
 void AxisPlan::release() {
     if (d_tw) cudaFree(d_tw);
     if (d_chirp) cudaFree(d_chirp);
     if (d_bfilt) cudaFree(d_bfilt);
+    if (d_tw64) cudaFree(d_tw64);
+    if (d_chirp64) cudaFree(d_chirp64);
+    if (d_bfilt64) cudaFree(d_bfilt64);
     d_tw = d_chirp = d_bfilt = nullptr;
+    d_tw64 = d_chirp64 = d_bfilt64 = nullptr;
     radix.clear();
+}
+
+AxisDev<double> AxisPlan::dev64() const {
+    AxisDev<double> a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.L = L; a.npass = (int)radix.size();
+    for (int i = 0; i < a.npass; ++i) a.radix[i] = radix[i];
+    a.bluestein = bluestein ? 1 : 0;
+    a.tw = d_tw64; a.chirp = d_chirp64; a.bfilt = d_bfilt64;
+    return a;
 }
 
 AxisDev<float> AxisPlan::dev() const {

@@ -43,10 +43,15 @@ struct AxisPlan {
     Cx<float>* d_tw = nullptr;
     Cx<float>* d_chirp = nullptr;
     Cx<float>* d_bfilt = nullptr;
+    Cx<double>* d_tw64 = nullptr;       // float64 tables, built on demand (build64)
+    Cx<double>* d_chirp64 = nullptr;
+    Cx<double>* d_bfilt64 = nullptr;
 
     void build(int n);          // allocates device tables on the current device
+    void build64();             // additionally the float64 tables (precision = 64 mode)
     void release();
     AxisDev<float> dev() const;
+    AxisDev<double> dev64() const;
     std::string describe() const;
 };
 

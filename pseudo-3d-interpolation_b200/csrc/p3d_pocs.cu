@@ -3,6 +3,8 @@
 #include "p3d_pocs_kernels.cuh"
 #include "p3d_pocs_spec.cuh"
 #include "p3d_pocs_launch.h"
+#include "p3d_pocs_f64.h"
+#include "p3d_schedule.h"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -48,6 +50,8 @@ struct p3d_plan {
     size_t col_smem = 0, row_smem = 0;
     SpecKernels spec{};              // specialised register-resident kernels when available
     bool force_generic = false;
+    int precision = 32;              // 32: fp32 fast path, 64: float64 state mode (p3d_pocs_f64.cu)
+    F64Runner* f64 = nullptr;
     int64_t max_slices = 0;
     int band_slices = 0;
     int n_lanes = 0;                 // 0 = auto
@@ -239,57 +243,14 @@ __global__ void k_pick_tau(const unsigned long long* sorted_desc, const SliceSta
     }
 }
 
-// ---- host schedule: get_threshold_decay in double (functions/POCS.py:286-362) -------------------------
-typedef std::complex<double> cd;
-
-// returns false when the schedule is data-driven (taken from device order statistics instead)
-void host_schedule(const p3d_pocs_params& pr, const SliceStats& st, int64_t size, std::vector<cd>& tau, bool& is_real) {
-    const int niter = pr.niter;
-    tau.assign(niter, cd(0, 0));
-    is_real = false;
-    const double dn = (double)(niter - 1);
-    if (pr.thresh_model == P3D_MODEL_INVERSE_PROPORTIONAL) {
-        is_real = true;
-        float fmax, fmin; unsigned int ub = st.maxabs_bits, lb = st.minabs_bits;
-        memcpy(&fmax, &ub, 4); memcpy(&fmin, &lb, 4);
-        const double vmax = fmax, vmin = fmin, q = pr.q;
-        const double nq = std::pow((double)niter, q);
-        const double a = (nq * (vmax - vmin)) / (nq - 1), b = (nq * vmin - vmax) / (nq - 1);
-        for (int k = 0; k < niter; ++k) tau[k] = cd(a / std::pow((double)(k + 1), q) + b, 0.0);
-    } else {
-        cd z(f32_from_ordered((unsigned int)(st.lexmax_key >> 32)), f32_from_ordered((unsigned int)(st.lexmax_key & 0xffffffffu)));
-        if (pr.absmax_threshold) { float fmax; unsigned int ub = st.maxabs_bits; memcpy(&fmax, &ub, 4); z = cd(fmax, 0.0); }
-        cd tmax, tmin;
-        bool real_sched = false;
-        if (pr.decay_factors) { tmax = cd(pr.p_max, 0); tmin = cd(pr.p_min, 0); real_sched = true; }
-        else {
-            tmax = pr.p_max * z;
-            tmin = pr.p_min_adaptive ? cd(0.01 * std::sqrt(st.sumsq / (double)size), 0.0) : pr.p_min * z;
-            real_sched = pr.absmax_threshold != 0;
-        }
-        is_real = real_sched;
-        for (int k = 0; k < niter; ++k) {
-            const double mu = (double)k / dn;        // niter == 1 -> 0/0 = nan, as in the reference
-            if (pr.thresh_model == P3D_MODEL_LINEAR) {
-                tau[k] = tmax - (tmax - tmin) * mu;
-            } else if (pr.thresh_model == P3D_MODEL_EXPONENTIAL) {
-                if (real_sched) {
-                    const double c = std::log(tmin.real() / tmax.real());
-                    tau[k] = cd(tmax.real() * std::exp(c * std::pow(mu, pr.q)), 0.0);
-                } else {
-                    const cd c = std::log(tmin / tmax);
-                    tau[k] = tmax * std::exp(c * std::pow(mu, pr.q));
-                }
-            }
-        }
-    }
-}
-
-void apply_sqrt_decay(std::vector<cd>& tau, bool is_real) {
-    for (auto& t : tau) {
-        if (is_real) t = cd(std::sqrt(t.real()), 0.0);   // nan for negative values, like numpy
-        else t = std::sqrt(t);
-    }
+// float statistics of a slice -> inputs of the host schedule (p3d_schedule.h)
+ScheduleStats stats_f32(const SliceStats& st) {
+    ScheduleStats s;
+    s.z = cd(f32_from_ordered((unsigned int)(st.lexmax_key >> 32)), f32_from_ordered((unsigned int)(st.lexmax_key & 0xffffffffu)));
+    float fmax, fmin; unsigned int ub = st.maxabs_bits, lb = st.minabs_bits;
+    memcpy(&fmax, &ub, 4); memcpy(&fmin, &lb, 4);
+    s.vmax = fmax; s.vmin = fmin; s.sumsq = st.sumsq;
+    return s;
 }
 
 void ensure_mask(p3d_plan* P, const uint8_t* mask, int64_t bytes, int mem, cudaStream_t st, const uint8_t** dmask) {
@@ -426,7 +387,7 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     if (!data_driven) {
         for (int64_t i = 0; i < count; ++i) {
             bool is_real = false;
-            host_schedule(pr, L.h_stats[i], ne, tau, is_real);
+            host_schedule(pr, stats_f32(L.h_stats[i]), ne, tau, is_real);
             if (pr.sqrt_decay) apply_sqrt_decay(tau, is_real);
             for (int k = 0; k < niter; ++k) {
                 L.h_tau[i * niter + k] = cmake<float>((float)tau[k].real(), (float)tau[k].imag());
@@ -446,12 +407,8 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
         for (int64_t i = 0; i < count; ++i) {
             L.h_stop[i] = L.h_stats[i].nnz == 0 ? -1 : 0;
             if (L.h_stop[i]) continue;
-            const SliceStats& ss = L.h_stats[i];
-            cd z(f32_from_ordered((unsigned int)(ss.lexmax_key >> 32)), f32_from_ordered((unsigned int)(ss.lexmax_key & 0xffffffffu)));
-            if (pr.absmax_threshold) { float fmax; unsigned int ub = ss.maxabs_bits; memcpy(&fmax, &ub, 4); z = cd(fmax, 0.0); }
-            cd tmax = pr.decay_factors ? cd(pr.p_max, 0) : pr.p_max * z;
-            cd tmin = pr.decay_factors ? cd(pr.p_min, 0)
-                                       : (pr.p_min_adaptive ? cd(0.01 * std::sqrt(ss.sumsq / (double)ne), 0.0) : pr.p_min * z);
+            cd tmin, tmax;
+            schedule_bounds(pr, stats_f32(L.h_stats[i]), ne, tmin, tmax);
             const unsigned long long lo = lex_key((float)tmin.real(), (float)tmin.imag());
             const unsigned long long hi = lex_key((float)tmax.real(), (float)tmax.imag());
             unsigned long long* keys = reinterpret_cast<unsigned long long*>(OUT + i * ne);
@@ -539,6 +496,18 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     if (spm <= 0) spm = n_slices;
     DeviceGuard guard(P->device);
 
+    if (P->precision == 64) {
+        if (!P->f64) P->f64 = f64_create(P->device, P->n1, P->n2, &P->ax1, &P->ax2, P->smem_optin);
+        if (P->lanes.empty()) P->lanes.resize(1);
+        if (!P->lanes[0].stream) P3D_CUDA(cudaStreamCreateWithFlags(&P->lanes[0].stream, cudaStreamNonBlocking));
+        const uint8_t* dmask = nullptr;
+        if (!schedule_only) {
+            const int64_t n_masks = (n_slices + spm - 1) / spm;
+            ensure_mask(P, mask, n_masks * (int64_t)P->n1 * P->n2, x_mem, P->lanes[0].stream, &dmask);
+        }
+        return f64_run(P->f64, pr, (const Cx<float>*)x, x_mem, dmask, spm, (Cx<float>*)out, out_mem, n_slices, niter_out,
+                       cost_out, costs_out, tau_out, schedule_only, P->max_slices);
+    }
     const bool host_in = x_mem == P3D_MEM_HOST, host_out = (out_mem == P3D_MEM_HOST) || schedule_only;
     const int lanes = P->n_lanes > 0 ? P->n_lanes : ((host_in || host_out) ? 2 : 1);
     if ((int)P->lanes.size() < lanes) P->lanes.resize(lanes);
@@ -629,6 +598,7 @@ int p3d_plan_destroy(p3d_plan* P) {
     P->ax1.release(); P->ax2.release();
     if (P->d_mask) cudaFree(P->d_mask);
     if (P->d_mbits) cudaFree(P->d_mbits);
+    if (P->f64) f64_destroy(P->f64);
     if (P->spec_tw_cols) cudaFree(P->spec_tw_cols);
     if (P->spec_tw_rows) cudaFree(P->spec_tw_rows);
     if (P->cub_temp) cudaFree(P->cub_temp);
@@ -723,6 +693,7 @@ int p3d_plan_describe(p3d_plan* P, char* buf, int64_t buflen) {
          " thr, smem " + std::to_string(P->row_smem) + " B";
     s += std::string("; cols_iter=") + ((P->spec.cols_iter && !P->force_generic) ? P->spec.cols_name : "generic");
     s += std::string("; rows_iter=") + ((P->spec.rows_iter && !P->force_generic) ? P->spec.rows_name : "generic");
+    s += "; precision=" + std::to_string(P->precision);
     s += "; band_slices=" + std::to_string(P->band_slices) + "; sms=" + std::to_string(P->sm_count);
     snprintf(buf, (size_t)buflen, "%s", s.c_str());
     return P3D_OK;
@@ -733,6 +704,10 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     if (!strcmp(key, "band_slices")) P->band_slices = (int)value;
     else if (!strcmp(key, "force_generic")) P->force_generic = value != 0;
     else if (!strcmp(key, "lanes")) P->n_lanes = (int)value;
+    else if (!strcmp(key, "precision")) {
+        if (value != 32 && value != 64) { set_error("precision must be 32 or 64"); return P3D_ERR_BAD_ARG; }
+        P->precision = (int)value;
+    }
     else if (!strcmp(key, "spec_variant")) {
         try { DeviceGuard g(P->device); install_spec(P, (int)value); } catch (const P3dFail& f) { return f.code; }
     }

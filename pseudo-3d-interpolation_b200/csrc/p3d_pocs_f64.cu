@@ -1,0 +1,239 @@
+// Float64 state mode of the POCS path ("precision" = 64): complex128 iterate, spectrum and
+// thresholds on the device, generic kernels instantiated for double.  Same ABI as the fp32 path
+// (complex64 in, complex64 out = the float64 result rounded once at the end, like the reference's
+// np.vectorize(otypes=[cube.dtype]) cast, cube_POCS_interpolation_3D.py:324).  One stream,
+// chunked by device memory; built for exactness, not for speed.
+#include "p3d_pocs_f64.h"
+#include "p3d_pocs_launch.h"
+#include "p3d_schedule.h"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+namespace p3d {
+
+struct F64Runner {
+    int device = 0, n1 = 0, n2 = 0;
+    AxisPlan* ax1 = nullptr; AxisPlan* ax2 = nullptr;
+    GenericCfg cfg{};
+    cudaStream_t st = nullptr;
+    int64_t cap = 0; int niter_cap = 0;
+    Cx<double>* W = nullptr; Cx<double>* D = nullptr; Cx<double>* OUT = nullptr; Cx<double>* tau = nullptr;
+    Cx<float>* io32 = nullptr;           // complex64 staging for host input / output
+    double* S = nullptr; int* stop = nullptr; SliceStats* stats = nullptr;
+    std::vector<Cx<double>> h_tau; std::vector<double> h_S; std::vector<int> h_stop; std::vector<SliceStats> h_stats;
+};
+
+static void f64_free_buffers(F64Runner* R) {
+    void* ptrs[] = {R->W, R->D, R->OUT, R->tau, R->io32, R->S, R->stop, R->stats};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    R->W = R->D = R->OUT = R->tau = nullptr; R->io32 = nullptr; R->S = nullptr; R->stop = nullptr; R->stats = nullptr;
+    R->cap = 0; R->niter_cap = 0;
+}
+
+F64Runner* f64_create(int device, int n1, int n2, AxisPlan* ax1, AxisPlan* ax2, size_t smem_optin) {
+    F64Runner* R = new F64Runner();
+    try {
+        R->device = device; R->n1 = n1; R->n2 = n2; R->ax1 = ax1; R->ax2 = ax2;
+        ax1->build64(); ax2->build64();
+        const size_t budget = smem_optin - 2048, two = (228 * 1024) / 2 - 2048;
+        const size_t es = sizeof(Cx<double>);
+        const int L1 = ax1->L, L2 = ax2->L;
+        int C = 8;
+        while (C > 1 && (size_t)2 * L1 * C * es > two) C >>= 1;
+        if (C < 2) { C = 2; while (C > 1 && (size_t)2 * L1 * C * es > budget) C >>= 1; }
+        P3D_REQUIRE((size_t)2 * L1 * C * es <= budget, P3D_ERR_NOT_IMPLEMENTED, "iline axis %d too long for the float64 mode", n1);
+        C = std::min(C, std::max(1, n2));
+        const int pitch2 = L2 + 1;
+        int RB = 8;
+        while (RB > 1 && (size_t)2 * pitch2 * RB * es > two) RB >>= 1;
+        P3D_REQUIRE((size_t)2 * pitch2 * RB * es <= budget, P3D_ERR_NOT_IMPLEMENTED, "xline axis %d too long for the float64 mode", n2);
+        RB = std::min(RB, std::max(1, n1));
+        PocsGeom& G = R->cfg.geom;
+        G.n1 = n1; G.n2 = n2; G.C = C; G.RB = RB; G.pitch2 = pitch2; G.slices_per_mask = 1;
+        R->cfg.col_smem = (size_t)2 * L1 * C * es; R->cfg.row_smem = (size_t)2 * pitch2 * RB * es;
+        auto pick = [](long elems) { long t = ((elems / 8 + 31) / 32) * 32; return (int)std::min<long>(512, std::max<long>(128, t)); };
+        R->cfg.col_threads = pick((long)L1 * C); R->cfg.row_threads = pick((long)L2 * RB);
+        { cudaError_t e = generic64_configure(R->cfg); P3D_CUDA(e); }
+        P3D_CUDA(cudaStreamCreateWithFlags(&R->st, cudaStreamNonBlocking));
+    } catch (...) { f64_destroy(R); throw; }
+    return R;
+}
+
+void f64_destroy(F64Runner* R) {
+    if (!R) return;
+    f64_free_buffers(R);
+    if (R->st) cudaStreamDestroy(R->st);
+    delete R;
+}
+
+static void f64_ensure(F64Runner* R, int64_t n_slices, int niter, int64_t max_slices) {
+    const int64_t ne = (int64_t)R->n1 * R->n2;
+    int64_t want = n_slices;
+    if (max_slices > 0) want = std::min(want, max_slices);
+    if (R->cap >= want && R->niter_cap >= niter) return;
+    f64_free_buffers(R);
+    size_t free_b = 0, total_b = 0;
+    P3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double per_slice = (double)ne * (3 * sizeof(Cx<double>) + sizeof(Cx<float>));
+    int64_t cap = (int64_t)((double)free_b * 0.8 / per_slice);
+    cap = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(cap, want), 30000));
+    P3D_CUDA(cudaMalloc(&R->W, sizeof(Cx<double>) * ne * cap));
+    P3D_CUDA(cudaMalloc(&R->D, sizeof(Cx<double>) * ne * cap));
+    P3D_CUDA(cudaMalloc(&R->OUT, sizeof(Cx<double>) * ne * cap));
+    P3D_CUDA(cudaMalloc(&R->io32, sizeof(Cx<float>) * ne * cap));
+    P3D_CUDA(cudaMalloc(&R->tau, sizeof(Cx<double>) * cap * niter));
+    P3D_CUDA(cudaMalloc(&R->S, sizeof(double) * cap * (niter + 1)));
+    P3D_CUDA(cudaMalloc(&R->stop, sizeof(int) * cap));
+    P3D_CUDA(cudaMalloc(&R->stats, sizeof(SliceStats) * cap));
+    R->cap = cap; R->niter_cap = niter;
+    R->h_tau.resize((size_t)cap * niter); R->h_S.resize((size_t)cap * (niter + 1)); R->h_stop.resize(cap); R->h_stats.resize(cap);
+}
+
+// numpy ordering of complex numbers
+static inline bool lex_less(const cd& a, const cd& b) { return a.real() < b.real() || (a.real() == b.real() && a.imag() < b.imag()); }
+
+int f64_run(F64Runner* R, const p3d_pocs_params* prp, const Cx<float>* x, int x_mem, const uint8_t* dmask, int64_t spm,
+            Cx<float>* out, int out_mem, int64_t n_slices, int32_t* niter_out, double* cost_out, double* costs_out,
+            double* tau_out, bool schedule_only, int64_t max_slices) {
+    const p3d_pocs_params& pr = *prp;
+    const int niter = pr.niter;
+    const int64_t ne = (int64_t)R->n1 * R->n2;
+    f64_ensure(R, n_slices, niter, max_slices);
+    cudaStream_t st = R->st;
+    const bool data_driven = pr.thresh_model == P3D_MODEL_DATA_DRIVEN;
+    const bool adaptive = pr.version == P3D_VERSION_ADAPTIVE;
+    const AxisDev<double> a1 = R->ax1->dev64(), a2 = R->ax2->dev64();
+    R->cfg.geom.slices_per_mask = (int)std::min<int64_t>(spm, 0x7fffffff);
+
+    for (int64_t first = 0; first < n_slices; first += R->cap) {
+        const int64_t count = std::min<int64_t>(R->cap, n_slices - first);
+        // ---- input -> complex128
+        if (x_mem == P3D_MEM_HOST) {
+            P3D_CUDA(cudaMemcpyAsync(R->io32, x + first * ne, sizeof(Cx<float>) * ne * count, cudaMemcpyHostToDevice, st));
+            convert_c64_to_c128(R->io32, R->D, ne * count, st);
+        } else {
+            convert_c64_to_c128(x + first * ne, R->D, ne * count, st);
+        }
+        P3D_CUDA(cudaMemsetAsync(R->S, 0, sizeof(double) * count * (niter + 1), st));
+        P3D_CUDA(cudaMemsetAsync(R->stop, 0, sizeof(int) * count, st));
+        for (int64_t i = 0; i < count; ++i) {
+            memset(&R->h_stats[i], 0, sizeof(SliceStats));
+            R->h_stats[i].minabs_bits = 0x7f800000u;
+            R->h_stats[i].minabs64_key = ~0ull;
+        }
+        P3D_CUDA(cudaMemcpyAsync(R->stats, R->h_stats.data(), sizeof(SliceStats) * count, cudaMemcpyHostToDevice, st));
+        P3D_CUDA(cudaStreamSynchronize(st));      // h_stats is pageable and reused below
+
+        BandArgs<double> A;
+        memset(&A, 0, sizeof(A));
+        A.mask = dmask; A.mbits = nullptr; A.niter = niter; A.eps = pr.eps; A.alpha = pr.alpha;
+        A.inv_n = 1.0 / ((double)R->n1 * (double)R->n2);
+        A.W = R->W; A.D = R->D; A.OUT = R->OUT; A.first_slice = first; A.tau = R->tau; A.S = R->S; A.stop = R->stop; A.stats = R->stats;
+        const int64_t band_max = 32768;
+
+        for (int64_t b0 = 0; b0 < count; b0 += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, count - b0);
+            BandArgs<double> B = A;
+            B.W += b0 * ne; B.D += b0 * ne; B.OUT += b0 * ne; B.first_slice += b0; B.S += b0 * (niter + 1); B.stop += b0; B.stats += b0;
+            B.adaptive = 0; B.accum = 1; B.store_x0 = 1;
+            generic64_rows_init(R->cfg, a2, B, nb, st);
+            generic64_cols_stats(R->cfg, a1, B, nb, st);
+            generic64_lexmax_imag(B.OUT, B.stats, ne, nb, st);
+        }
+        P3D_CUDA(cudaGetLastError());
+        P3D_CUDA(cudaMemcpyAsync(R->h_stats.data(), R->stats, sizeof(SliceStats) * count, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaStreamSynchronize(st));
+
+        // ---- schedule (host, double)
+        std::vector<cd> tau;
+        std::vector<cd> x0;
+        for (int64_t i = 0; i < count; ++i) {
+            const SliceStats& ss = R->h_stats[i];
+            R->h_stop[i] = ss.nnz == 0 ? -1 : 0;
+            ScheduleStats s;
+            s.z = cd(f64_from_ordered(ss.re64_key), f64_from_ordered(ss.im64_key));
+            s.sumsq = ss.sumsq; s.vmax = f64_from_ordered(ss.maxabs64_key); s.vmin = f64_from_ordered(ss.minabs64_key);
+            bool is_real = false;
+            if (!data_driven) {
+                host_schedule(pr, s, ne, tau, is_real);
+            } else {
+                tau.assign(niter, cd(0, 0));
+                if (!R->h_stop[i]) {
+                    cd tmin, tmax;
+                    schedule_bounds(pr, s, ne, tmin, tmax);
+                    x0.resize((size_t)ne);
+                    P3D_CUDA(cudaMemcpy(x0.data(), R->OUT + i * ne, sizeof(Cx<double>) * ne, cudaMemcpyDeviceToHost));
+                    std::vector<cd> cand;
+                    cand.reserve((size_t)ne / 2);
+                    for (const cd& v : x0) if (lex_less(tmin, v) && lex_less(v, tmax)) cand.push_back(v);
+                    P3D_REQUIRE(!cand.empty(), P3D_ERR_NUMERIC, "data-driven schedule: no coefficient between tau_min and tau_max in slice %lld", (long long)(first + i));
+                    std::sort(cand.begin(), cand.end(), [](const cd& a, const cd& b) { return lex_less(b, a); });   // descending
+                    const double nv1 = (double)(cand.size() - 1);
+                    tau[0] = cand[0];
+                    for (int k = 1; k < niter; ++k) {
+                        long long idx = (long long)std::ceil((double)((long long)k * (long long)(cand.size() - 1)) / (double)(niter - 1));
+                        if (idx > (long long)nv1) idx = (long long)nv1;
+                        tau[k] = cand[(size_t)idx];
+                    }
+                }
+            }
+            if (pr.sqrt_decay) apply_sqrt_decay(tau, is_real);
+            for (int k = 0; k < niter; ++k) {
+                R->h_tau[i * niter + k] = cmake<double>(tau[k].real(), tau[k].imag());
+                if (tau_out) { tau_out[((first + i) * niter + k) * 2] = tau[k].real(); tau_out[((first + i) * niter + k) * 2 + 1] = tau[k].imag(); }
+            }
+        }
+        if (schedule_only) continue;
+        P3D_CUDA(cudaMemcpyAsync(R->tau, R->h_tau.data(), sizeof(Cx<double>) * count * niter, cudaMemcpyHostToDevice, st));
+        P3D_CUDA(cudaMemcpyAsync(R->stop, R->h_stop.data(), sizeof(int) * count, cudaMemcpyHostToDevice, st));
+        P3D_CUDA(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < count; ++i)
+            if (R->h_stop[i] < 0)
+                P3D_CUDA(cudaMemcpyAsync(R->OUT + i * ne, R->D + i * ne, sizeof(Cx<double>) * ne, cudaMemcpyDeviceToDevice, st));
+
+        for (int64_t b0 = 0; b0 < count; b0 += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, count - b0);
+            BandArgs<double> B = A;
+            B.W += b0 * ne; B.D += b0 * ne; B.OUT += b0 * ne; B.first_slice += b0; B.tau += b0 * niter; B.S += b0 * (niter + 1); B.stop += b0; B.stats += b0;
+            B.adaptive = adaptive ? 1 : 0;
+            if (adaptive) { B.accum = 0; B.store_x0 = 0; generic64_rows_init(R->cfg, a2, B, nb, st); }
+            for (int k = 0; k < niter; ++k) {
+                B.k = k; B.last = (k == niter - 1) ? 1 : 0;
+                B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
+                generic64_cols_iter(R->cfg, a1, B, nb, pr.thresh_op, st);
+                generic64_rows_iter(R->cfg, a2, B, nb, st);
+            }
+        }
+        P3D_CUDA(cudaGetLastError());
+
+        // ---- results: one rounding to complex64
+        if (out_mem == P3D_MEM_HOST) {
+            convert_c128_to_c64(R->OUT, R->io32, ne * count, st);
+            P3D_CUDA(cudaMemcpyAsync(out + first * ne, R->io32, sizeof(Cx<float>) * ne * count, cudaMemcpyDeviceToHost, st));
+        } else {
+            convert_c128_to_c64(R->OUT, out + first * ne, ne * count, st);
+        }
+        P3D_CUDA(cudaMemcpyAsync(R->h_S.data(), R->S, sizeof(double) * count * (niter + 1), cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(R->h_stop.data(), R->stop, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < count; ++i) {
+            const int64_t s = first + i;
+            const int sp = R->h_stop[i];
+            const int nit = sp < 0 ? 0 : (sp > 0 ? sp : niter);
+            if (niter_out) niter_out[s] = nit;
+            const double* S = R->h_S.data() + i * (niter + 1);
+            double last = 0.0;
+            for (int k = 0; k < niter; ++k) {
+                double c = std::numeric_limits<double>::quiet_NaN();
+                if (k < nit) { const double d = S[k + 1] - S[k]; c = (d * d) / (S[k + 1] * S[k + 1]); last = c; }
+                if (costs_out) costs_out[s * niter + k] = c;
+            }
+            if (cost_out) cost_out[s] = last;
+        }
+    }
+    return P3D_OK;
+}
+
+}  // namespace p3d

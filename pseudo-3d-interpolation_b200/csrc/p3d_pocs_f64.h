@@ -1,0 +1,15 @@
+// Float64 state mode runner (p3d_pocs_f64.cu).
+#pragma once
+#include "p3d_host.h"
+
+namespace p3d {
+
+struct F64Runner;
+F64Runner* f64_create(int device, int n1, int n2, AxisPlan* ax1, AxisPlan* ax2, size_t smem_optin);
+void f64_destroy(F64Runner* R);
+// x / out: complex64 in host or device memory (x_mem / out_mem); dmask: DEVICE pointer
+int f64_run(F64Runner* R, const p3d_pocs_params* pr, const Cx<float>* x, int x_mem, const uint8_t* dmask, int64_t spm,
+            Cx<float>* out, int out_mem, int64_t n_slices, int32_t* niter_out, double* cost_out, double* costs_out,
+            double* tau_out, bool schedule_only, int64_t max_slices);
+
+}  // namespace p3d

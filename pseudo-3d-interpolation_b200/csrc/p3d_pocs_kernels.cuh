@@ -20,7 +20,29 @@ struct SliceStats {
     unsigned int minabs_bits;        // min |X0|
     unsigned long long nnz;          // count_nonzero(x)
     unsigned long long n_cand;       // data-driven: number of candidates inside (tau_min, tau_max)
+    // float64 state mode only (ordered keys of doubles)
+    unsigned long long re64_key;     // max real part of X0
+    unsigned long long im64_key;     // max imaginary part among the elements with that real part
+    unsigned long long maxabs64_key; // max |X0|
+    unsigned long long minabs64_key; // min |X0|
 };
+
+__host__ __device__ __forceinline__ unsigned long long f64_ordered(double f) {
+#ifdef __CUDA_ARCH__
+    unsigned long long u = (unsigned long long)__double_as_longlong(f);
+#else
+    unsigned long long u; memcpy(&u, &f, 8);
+#endif
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double f64_from_ordered(unsigned long long u) {
+    u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double f; memcpy(&f, &u, 8); return f;
+#endif
+}
 
 __host__ __device__ __forceinline__ unsigned int f32_ordered(float f) {
 #ifdef __CUDA_ARCH__
@@ -190,6 +212,31 @@ __global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_
             atomicAdd(&A.stats[s].sumsq, ss);
             atomicMax(&A.stats[s].maxabs_bits, amax);
             atomicMin(&A.stats[s].minabs_bits, amin);
+        }
+        if (sizeof(T) == 8) {
+            // float64 state: exact keys (the imaginary tie-break runs as a second pass over X0)
+            unsigned long long rk = 0ull, ak = 0ull, ik = ~0ull;
+            double ss64 = 0.0;
+            for (int w = tid; w < tot; w += nth) {
+                const int i = w / nc, c = w - i * nc;
+                const Cx<T> v = X[i * G.C + c];
+                const unsigned long long k1 = f64_ordered((double)v.x);
+                rk = k1 > rk ? k1 : rk;
+                const double r2 = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+                ss64 += r2;
+                const unsigned long long k2 = f64_ordered(sqrt(r2));
+                ak = k2 > ak ? k2 : ak; ik = k2 < ik ? k2 : ik;
+            }
+            rk = warp_max_u64(rk); ak = warp_max_u64(ak);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { unsigned long long w2 = __shfl_xor_sync(0xffffffffu, ik, o); ik = w2 < ik ? w2 : ik; }
+            ss64 = warp_sum(ss64) - ss;           // replace the float-accumulated sum by the double one
+            if ((tid & 31) == 0) {
+                atomicMax(&A.stats[s].re64_key, rk);
+                atomicMax(&A.stats[s].maxabs64_key, ak);
+                atomicMin(&A.stats[s].minabs64_key, ik);
+                atomicAdd(&A.stats[s].sumsq, ss64);
+            }
         }
         return;
     }

@@ -18,6 +18,7 @@ There is no CPU fallback: without the shared library or a CUDA device these func
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 import time
 from functools import partial
@@ -29,7 +30,7 @@ from . import _lib
 TRANSFORMS = ("FFT", "WAVELET", "SHEARLET", "CURVELET", "DCT")
 
 __all__ = ["POCS_algorithm", "POCS", "FPOCS", "APOCS", "get_threshold_decay", "threshold", "pocs_cube",
-           "PocsPlan", "make_params", "mask_from_fold", "fft2", "ifft2"]
+           "PocsPlan", "make_params", "mask_from_fold", "fft2", "ifft2", "set_default_precision"]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -102,7 +103,9 @@ def mask_from_fold(fold):
 class PocsPlan:
     """One ``p3d_plan`` (one GPU, one slice shape).  Not re-entrant; use one per thread/GPU."""
 
-    def __init__(self, n_iline, n_xline, device=0, max_slices=0, band_slices=0):
+    def __init__(self, n_iline, n_xline, device=0, max_slices=0, band_slices=0, precision=32):
+        """``precision``: 32 = fp32 fast path (default); 64 = float64 state mode (complex128
+        iterate on the device, result rounded once to complex64) for bit-level-robust parity."""
         lib = _lib.load()
         _lib.require_gpu()
         self.n_iline, self.n_xline, self.device = int(n_iline), int(n_xline), int(device)
@@ -110,6 +113,9 @@ class PocsPlan:
         _lib.check(lib.p3d_plan_create(C.byref(h), self.device, self.n_iline, self.n_xline, int(max_slices), int(band_slices)))
         self._h = h
         self._lock = threading.Lock()
+        self.precision = int(precision)
+        if self.precision != 32:
+            self.set_option("precision", self.precision)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -211,14 +217,24 @@ class PocsPlan:
 
 _PLANS = {}
 _PLANS_LOCK = threading.Lock()
+_DEFAULT_PRECISION = [int(os.environ.get("P3D_PRECISION", "32"))]
 
 
-def get_plan(n_iline, n_xline, device=0) -> PocsPlan:
-    key = (int(n_iline), int(n_xline), int(device))
+def set_default_precision(bits: int):
+    """32 (fp32 fast path) or 64 (float64 state mode) for POCS_algorithm / pocs_cube calls that do
+    not say otherwise.  Also settable with the environment variable P3D_PRECISION."""
+    if int(bits) not in (32, 64):
+        raise ValueError("precision must be 32 or 64")
+    _DEFAULT_PRECISION[0] = int(bits)
+
+
+def get_plan(n_iline, n_xline, device=0, precision=None) -> PocsPlan:
+    precision = _DEFAULT_PRECISION[0] if precision is None else int(precision)
+    key = (int(n_iline), int(n_xline), int(device), precision)
     with _PLANS_LOCK:
         p = _PLANS.get(key)
         if p is None:
-            p = _PLANS[key] = PocsPlan(*key[:2], device=key[2])
+            p = _PLANS[key] = PocsPlan(key[0], key[1], device=key[2], precision=precision)
         return p
 
 
@@ -412,7 +428,7 @@ def band_bounds(n_slices: int, n_parts: int):
     return [(min(i * per, n_slices), min((i + 1) * per, n_slices)) for i in range(n_parts)]
 
 
-def pocs_cube(cube, fold_or_mask, devices=None, out=None, results=None, **metadata):
+def pocs_cube(cube, fold_or_mask, devices=None, out=None, results=None, precision=None, **metadata):
     """POCS over every slice of ``cube`` (n_slices, n_iline, n_xline).
 
     ``cube`` complex64 (frequency domain) or float32 (time domain, iterated as complex and
@@ -452,7 +468,7 @@ def pocs_cube(cube, fold_or_mask, devices=None, out=None, results=None, **metada
         try:
             if hi <= lo:
                 return
-            plan = get_plan(n1, n2, dev)
+            plan = get_plan(n1, n2, dev, precision)
             _, info = plan.run(xin[lo:hi], mask, out=res[lo:hi], params=params)
             nit[lo:hi] = info["niterations"]
             cost[lo:hi] = info["cost"]

@@ -232,31 +232,80 @@ def test_full_size_config_slices(p3d):
         assert np.array_equal(y[:, obs], d[:, obs])
 
 
-def test_full_size_config_slices_soft(p3d):
-    """Same slices with the soft operator (continuous): fp32 holds 1e-4 against float64 --
-    except on slices where the reference's own choice of z = x_fwd.max() (largest REAL part,
-    SURVEY Q1) is a near tie: an fp32-sized perturbation then selects the other coefficient and
-    the whole schedule tau = p * z jumps (a discontinuity of the reference algorithm, visible in
-    the float64 oracle itself).  Such slices are identified from the float64 spectrum and only
-    bounded loosely."""
+def test_full_size_config_slices_soft_fp32(p3d):
+    """Soft operator, same slices, fp32 path.  With the reference's complex tau (Q1) even the
+    soft and garrote operators jump at |X| = Re(tau): just below the factor is clipped to 0, at
+    it the factor is -i Im(tau)/|X| != 0.  fp32 rounding can therefore flip single coefficients
+    exactly as for the hard operator, and the bound here is the flip bound (2e-3), not 1e-4; the
+    float64 state mode (next test) holds 1e-4 on the same input."""
     from pseudo_3d_interpolation_b200 import synth
-    ids = [20, 60, 100, 140, 200]
-    d, fold, c = synth.sparse_freq_slices(1, slice_ids=ids)
+    d, fold, c = synth.sparse_freq_slices(1, slice_ids=[20, 100, 200])
     params = dict(niter=c["niter"], thresh_op="soft", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-5)
     y = p3d.pocs_cube(d, fold, **params)
     ref = orc.pocs_cube(d, fold, **params)
-    n_strict = 0
-    for i in range(len(ids)):
-        re = np.sort(np.fft.fft2(d[i].astype(np.complex128)).real.ravel())
-        gap = (re[-1] - re[-2]) / abs(re[-1])
-        err = rel_l2(y[i], ref[i])
-        print(f"slice {ids[i]}: rel-L2 {err:.3e}, relative gap of the two largest real parts {gap:.2e}")
-        if gap > 1e-5:
-            n_strict += 1
-            assert err <= RTOL, (ids[i], err, gap)
-        else:
-            assert err <= 5e-3, (ids[i], err, gap)
-    assert n_strict >= 2
+    print(f"soft fp32 full size: rel-L2 {rel_l2(y, ref):.3e}")
+    assert rel_l2(y, ref) <= 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# float64 state mode: parity with the reference's float64 results at the 1e-4 of BASELINE.json
+# (in fact at complex64 rounding level) on every case, including the ill-conditioned ones
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_f64_mode_matches_reference_golden(case, golden, p3d):
+    x, mask = make_input(case)
+    n = case["name"]
+    ref = golden[f"{n}__y"]
+    plan = p3d.PocsPlan(x.shape[0], x.shape[1], precision=64)
+    y, info = plan.run(x.astype(np.complex64), mask, version=case.get("version", "regular"), want_costs=True, **case["params"])
+    nit = int(info["niterations"][0])
+    assert nit == int(golden[f"{n}__niterations"])
+    if nit == 0:
+        assert np.array_equal(y[0], x.astype(np.complex64))
+        return
+    got = y[0] if np.iscomplexobj(ref) else y[0].real
+    assert rel_l2(got, ref) <= 2e-7, rel_l2(got, ref)            # = one rounding to complex64
+    costs = info["costs"][0][:nit]
+    refc = golden[f"{n}__costs"]
+    big = refc > 1e-24
+    np.testing.assert_allclose(costs[big], refc[big], rtol=1e-6)
+
+
+def test_f64_mode_full_size_config_slices(p3d):
+    """configs 1 (5 slices, hard and soft) and 2 (1 slice) at full size: <= 1e-4 vs float64 reference."""
+    from pseudo_3d_interpolation_b200 import synth
+    for cfg, ids, ops in ((1, [20, 60, 100, 140, 200], ("hard", "soft")), (2, [300], ("hard",))):
+        d, fold, c = synth.sparse_freq_slices(cfg, slice_ids=ids)
+        for op in ops:
+            params = dict(niter=c["niter"], thresh_op=op, thresh_model=c["thresh_model"], eps=0.0, alpha=c["alpha"], p_max=0.99, p_min=1e-5)
+            y = p3d.pocs_cube(d, fold, precision=64, **params)
+            ref = orc.pocs_cube(d, fold, **params)
+            e = rel_l2(y, ref)
+            print(f"f64 mode config {cfg} {op}: cube rel-L2 {e:.3e}")
+            assert e <= RTOL, e
+            obs = orc.mask_from_fold(fold) == 1
+            assert np.array_equal(y[:, obs], d[:, obs])
+
+
+def test_f64_mode_ill_conditioned_spec_shape(p3d):
+    """256 x 256 hard / exponential, p_min = 1e-4, 12 iterations: fp32 (and the float64 oracle under a
+    1e-7 input perturbation) moves by 5e-3 here; the float64 mode reproduces the reference."""
+    x, mask = make_input(dict(seed=77, shape=(256, 256), keep=0.3, nwaves=5))
+    params = dict(niter=12, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-4)
+    ref = orc.pocs_slice(x.astype(np.complex128), mask, **params)
+    y, _ = p3d.PocsPlan(256, 256, precision=64).run(x, mask, **params)
+    assert rel_l2(y[0], ref) <= 2e-7, rel_l2(y[0], ref)
+
+
+def test_f64_mode_data_driven_and_schedule(p3d):
+    case = CASES[4]
+    x, mask = make_input(case)
+    plan = p3d.PocsPlan(*x.shape, precision=64)
+    X0 = np.fft.fft2(x.astype(np.complex128))
+    for model in ("data-driven", "exponential", "linear", "inverse_proportional"):
+        tau = plan.schedule(x, niter=11, thresh_model=model, p_max=0.99, p_min=1e-5)[0]
+        ref = orc.threshold_table(X0, 11, model, 0.99, 1e-5)
+        np.testing.assert_allclose(tau, ref, rtol=1e-10, atol=1e-12 * np.abs(ref).max())
 
 
 def test_per_cube_masks(p3d):
