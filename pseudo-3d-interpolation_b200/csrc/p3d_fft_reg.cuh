@@ -33,8 +33,23 @@ __host__ __device__ constexpr int exch_delta(int Ns, int R) {
     if (d < 0) d += 16;
     return d;
 }
-// storage needed per line (elements), upper bound over all exchanges
-__host__ __device__ constexpr int padded_line(int N) { return N + N / 6 + 16; }
+// storage needed per line (elements): the largest padded address over all exchanges, + 1
+template <int... Rs> struct PaddedLine {
+    static constexpr int value() {
+        const int r[] = {Rs...};
+        const int np = (int)sizeof...(Rs);
+        int n = 1;
+        for (int i = 0; i < np; ++i) n *= r[i];
+        int best = n, ns = 1;
+        for (int i = 0; i + 1 < np; ++i) {
+            const int b = ns * r[i];
+            const int need = n + (n / b - 1) * exch_delta(ns, r[i]);
+            best = need > best ? need : best;
+            ns = b;
+        }
+        return (best + 3) & ~3;        // keep rows of the column tile 32-byte aligned
+    }
+};
 
 // Accessor concept:
 //   static constexpr int STRIDE;            element stride of consecutive line positions
@@ -128,7 +143,7 @@ template <int N_, int E_, int... Rs> struct LinePlan {
     static constexpr int E = E_;
     static constexpr int T = N_ / E_;
     static constexpr int NEXCH = (int)sizeof...(Rs) - 1;      // shared-memory exchanges per transform
-    static constexpr int LINE = padded_line(N_);              // storage per line and buffer (elements)
+    static constexpr int LINE = PaddedLine<Rs...>::value();   // storage per line and buffer (elements)
     static constexpr int NPASS = (int)sizeof...(Rs);
     static void radices(int* out) { const int r[] = {Rs...}; for (int i = 0; i < NPASS; ++i) out[i] = r[i]; }
     // BUF0: buffer used by the first exchange; the next transform should start with (BUF0 + NEXCH) & 1

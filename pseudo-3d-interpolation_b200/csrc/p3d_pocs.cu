@@ -360,6 +360,7 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     A.inv_n = (float)(1.0 / ((double)P->n1 * (double)P->n2));
     const bool data_driven = pr.thresh_model == P3D_MODEL_DATA_DRIVEN;
     const bool adaptive = pr.version == P3D_VERSION_ADAPTIVE;
+    A.exact_tie = (pr.thresh_model == P3D_MODEL_INVERSE_PROPORTIONAL || data_driven || pr.decay_factors) ? 1 : 0;
     const int64_t band_max = 32768;
 
     auto band_args = [&](int64_t b0) {

@@ -87,6 +87,7 @@ template <typename T> struct BandArgs {
     double eps;
     T alpha, inv_n;
     int write_out, last, adaptive, store_x0, accum;
+    int exact_tie;               // thresholds derived from |X0| values (inverse-proportional): honour exact ties
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -95,9 +96,15 @@ template <typename T> struct BandArgs {
 __device__ __forceinline__ float p3d_rsqrt(float v) { return rsqrtf(v); }
 __device__ __forceinline__ double p3d_rsqrt(double v) { return 1.0 / sqrt(v); }
 
-template <int OP, typename T>
+template <int OP, typename T, bool TIE = true>
 __device__ __forceinline__ Cx<T> apply_threshold(Cx<T> X, const T a, const T b, const T t2re, const T t2im) {
     const T r2 = X.x * X.x + X.y * X.y;
+    if (OP == P3D_OP_HARD && !TIE) {
+        // schedules whose tau is p * z (linear / exponential): an exact tie |X| == Re(tau) has
+        // measure zero, the squared comparison decides
+        const bool kill = (a > T(0)) && (r2 < a * a);
+        return kill ? cmake<T>(T(0), T(0)) : X;
+    }
     if (OP == P3D_OP_HARD) {
         // |X| < a  <=>  |X|^2 < a^2 for a > 0 (never true for a <= 0): no square root on the hot
         // path.  Only when |X|^2 is within a few ulps of a^2 is the comparison redone on |X|

@@ -26,14 +26,19 @@ template <int RB, int LINE> struct RowAcc {
     __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (RB * LINE); }
 };
 
+// L2 prefetch of one 32-byte sector (the data of a tile that a later CTA will load)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// CTAs resident at a time (2 per SM on 148 SMs): the tile that far ahead is the one whose loads
+// should already be on their way when its CTA starts
+constexpr int P3D_PREFETCH_DISTANCE = 296;
+
 // ---- column kernel ---------------------------------------------------------------------------------
-template <typename LP, int C, int MINB>
+template <typename LP, int C, int MINB, bool PF>
 __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A, const int op) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     const int s = blockIdx.y;
-    if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) return;
     const int tid = threadIdx.x;
     const int c = tid % C, j = tid / C;
     const int col = blockIdx.x * C + c;
@@ -44,13 +49,29 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     Cx<float> v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(j + e * T) * G.n2] : cmake<float>(0.f, 0.f);
+    const Cx<float> tau = A.tau[(long long)s * A.niter + A.k];
+    // the (rare) early-exit test comes AFTER the loads were issued, so that its own dependent
+    // loads (stop flag, two sums) do not delay them
+    if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) return;
+    if (PF && (c & 3) == 0) {
+        // warm L2 with the tile of the CTA that will run P3D_PREFETCH_DISTANCE blocks later
+        const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + P3D_PREFETCH_DISTANCE;
+        const long long by = lin / gridDim.x, bx = lin - by * gridDim.x;
+        if (by < gridDim.y && bx * C + c < G.n2) {
+            const Cx<float>* nx = A.W + by * (long long)N * G.n2 + bx * C + c;
+#pragma unroll
+            for (int e = 0; e < E; ++e) prefetch_l2(nx + (long long)(j + e * T) * G.n2);
+        }
+    }
 
     LP::template fft<-1, 0, float>(v, acc, j, tw);
 
-    const Cx<float> tau = A.tau[(long long)s * A.niter + A.k];
     const float a = tau.x, b = tau.y;
     const float t2re = a * a - b * b, t2im = 2.f * a * b;
-    if (op == P3D_OP_HARD) {
+    if (op == P3D_OP_HARD && !A.exact_tie) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float, false>(v[e], a, b, t2re, t2im);
+    } else if (op == P3D_OP_HARD) {
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float>(v[e], a, b, t2re, t2im);
     } else if (op == P3D_OP_SOFT) {
@@ -70,7 +91,7 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
 }
 
 // ---- row kernel ----------------------------------------------------------------------------------
-template <typename LP, int RB, int MINB>
+template <typename LP, int RB, int MINB, bool PF>
 __global__ void __launch_bounds__(LP::T* RB, MINB)
 k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -78,7 +99,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     static_assert(E <= 32, "mask bits are packed into one 32-bit word");
     const int s = blockIdx.y;
-    if (A.stop[s] != 0) return;
+    const int stopped = A.stop[s];
     const int tid = threadIdx.x;
     const int j = tid % T, rr = tid / T;
     const int row = blockIdx.x * RB + rr;
@@ -92,9 +113,23 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     Cx<float> v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = ok ? Wp[e * T] : cmake<float>(0.f, 0.f);
+    if (PF && ok && (j & 3) == 0) {
+        // the observed data of this tile are needed after the inverse transform: start fetching now;
+        // and warm L2 with the W rows of the CTA that will run P3D_PREFETCH_DISTANCE blocks later
+#pragma unroll
+        for (int e = 0; e < E; ++e) prefetch_l2(Dp + e * T);
+        const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + P3D_PREFETCH_DISTANCE;
+        const long long by = lin / gridDim.x, bx = lin - by * gridDim.x;
+        if (by < gridDim.y && bx * RB + rr < G.n1) {
+            const Cx<float>* nx = A.W + by * (long long)G.n1 * N + (bx * RB + rr) * (long long)N + j;
+#pragma unroll
+            for (int e = 0; e < E; ++e) prefetch_l2(nx + e * T);
+        }
+    }
     // one packed mask word per thread (bit e <-> column j + e*T) rides along with the first loads
     const long long midx = (A.first_slice + s) / G.slices_per_mask;
     const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
+    if (stopped != 0) return;
 
     LP::template fft<+1, 0, float>(v, acc, j, tw);
 
@@ -153,27 +188,27 @@ __global__ void k_pack_mask(const uint8_t* __restrict__ mask, uint32_t* __restri
 }
 
 // ---- registry ----------------------------------------------------------------------------------------
-template <typename LP, int C, int MINB>
+template <typename LP, int C, int MINB, bool PF = false>
 static void launch_cols(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
     constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<float>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_cols_spec<LP, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cols_spec<LP, C, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n2 + C - 1) / C, ns);
-    k_cols_spec<LP, C, MINB><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
+    k_cols_spec<LP, C, MINB, PF><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
 }
-template <typename LP, int RB, int MINB>
+template <typename LP, int RB, int MINB, bool PF = false>
 static void launch_rows(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {
     constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_rows_spec<LP, RB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_rows_spec<LP, RB, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n1 + RB - 1) / RB, ns);
-    k_rows_spec<LP, RB, MINB><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+    k_rows_spec<LP, RB, MINB, PF><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
 }
 template <typename LP>
 static void launch_pack(const uint8_t* mask, uint32_t* bits, int n_masks, int n1, cudaStream_t st) {
@@ -220,9 +255,15 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
     switch (n_iline) {      // column transforms have the length of the iline axis
         case 1000:
             if (variant == 1) P3D_COLS(LP1000, 8, 1, "spec<1000,E10,10x10x10,C8,1cta>");
+            else if (variant == 6) P3D_COLS(LP1000, 4, 3, "spec<1000,E10,10x10x10,C4,3cta>");
+            else if (variant == 2) { k.cols_iter = launch_cols<LP1000, 4, 2, true>; k.cols_name = "spec<1000,E10,10x10x10,C4,2cta,l2prefetch>"; k.cols_radices = radices_of<LP1000>(); }
+            else if (variant == 4) P3D_COLS(LP1000, 2, 4, "spec<1000,E10,10x10x10,C2,4cta>");
             else              P3D_COLS(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta>");
             break;
-        case 2000: P3D_COLS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4>"); break;
+        case 2000:
+            if (variant == 4) P3D_COLS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,C2,2cta>");
+            else              P3D_COLS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4>");
+            break;
         case 256:  P3D_COLS(LP256, 16, 3, "spec<256,E16,16x16,C16>"); break;
         case 200:  P3D_COLS(LP200, 16, 4, "spec<200,E20,10x20,C16>"); break;
         default: break;
@@ -230,9 +271,15 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
     switch (n_xline) {      // row transforms have the length of the xline axis
         case 1000:
             if (variant == 1) P3D_ROWS(LP1000, 8, 1, "spec<1000,E10,10x10x10,RB8,1cta>");
-            else              P3D_ROWS(LP1000, 4, 2, "spec<1000,E10,10x10x10,RB4,2cta>");
+            else if (variant == 2) { k.rows_iter = launch_rows<LP1000, 4, 2, true>; k.rows_name = "spec<1000,E10,10x10x10,RB4,2cta,l2prefetch>"; k.rows_radices = radices_of<LP1000>(); k.pack_mask = launch_pack<LP1000>; k.rows_T = LP1000::T; }
+            else if (variant == 3) P3D_ROWS(LP1000, 4, 2, "spec<1000,E10,10x10x10,RB4,2cta>");
+            else if (variant == 5) P3D_ROWS(LP1000, 2, 4, "spec<1000,E10,10x10x10,RB2,4cta>");
+            else              P3D_ROWS(LP1000, 1, 7, "spec<1000,E10,10x10x10,RB1,7cta>");
             break;
-        case 2000: P3D_ROWS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,RB4>"); break;
+        case 2000:
+            if (variant == 3) P3D_ROWS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,RB4>");
+            else              P3D_ROWS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,RB2,2cta>");
+            break;
         case 256:  P3D_ROWS(LP256, 16, 3, "spec<256,E16,16x16,RB16>"); break;
         case 200:  P3D_ROWS(LP200, 16, 4, "spec<200,E20,10x20,RB16>"); break;
         default: break;

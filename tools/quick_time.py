@@ -32,7 +32,8 @@ def main():
     x1 = (base * mask).astype(np.complex64)
     x = np.broadcast_to(x1, (ns, n1, n2)).copy()
     x *= (1 + 0.01 * np.arange(ns, dtype=np.float32))[:, None, None]
-    plan = p3d.PocsPlan(n1, n2, band_slices=band)
+    precision = int(a[8]) if len(a) > 8 else 32
+    plan = p3d.PocsPlan(n1, n2, band_slices=band, precision=precision)
     if force_generic:
         plan.set_option("force_generic", 1)
     if len(a) > 7:
