@@ -334,7 +334,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom)
+            tj = json.load(open(tp)).get(dom)
+            traffic = tj["dram_bytes_per_slice"] * slices_per_launch if (tj and n1 == 1000 and n2 == 1000) else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
