@@ -178,6 +178,16 @@ def cpu_niter_for_budget(c, procs, budget_s=20.0):
 # ---------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    # Only the JSON line may reach stdout: C libraries (NCCL prints its version banner there)
+    # are redirected to stderr by swapping file descriptor 1; the JSON goes to the saved one.
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(saved_fd, "w")
+
+    def emit(obj):
+        json_out.write(json.dumps(obj) + "\n")
+        json_out.flush()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -208,7 +218,7 @@ def main():
                 "config": {"workload": cfg_workload, "inputs": "host numpy arrays"},
                 "cpu_baseline": {"value": value, "unit": "slice-iterations/s", "cores": procs, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "slice-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -396,7 +406,7 @@ def main():
                        "wall_ms_per_step": wall_ms_max / args.steps},
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
             "diag_cufft_chain": diag, "checksum": checksum}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

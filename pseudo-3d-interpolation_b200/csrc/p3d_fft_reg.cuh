@@ -153,4 +153,17 @@ template <int N_, int E_, int... Rs> struct LinePlan {
     }
 };
 
+// ---- shared-memory accessors ---------------------------------------------------------------------
+// Two buffers (see p3d_fft_reg.cuh).  Column tile: [addr][c], c fastest; row tile: [row][addr].
+template <int C, int LINE> struct ColAcc {
+    static constexpr int STRIDE = C;
+    Cx<float>* base;   // already offset by c
+    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (LINE * C); }
+};
+template <int RB, int LINE> struct RowAcc {
+    static constexpr int STRIDE = 1;
+    Cx<float>* base;   // already offset by the row
+    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (RB * LINE); }
+};
+
 }  // namespace p3d

@@ -13,19 +13,6 @@
 
 namespace p3d {
 
-// ---- shared-memory accessors ---------------------------------------------------------------------
-// Two buffers (see p3d_fft_reg.cuh).  Column tile: [addr][c], c fastest; row tile: [row][addr].
-template <int C, int LINE> struct ColAcc {
-    static constexpr int STRIDE = C;
-    Cx<float>* base;   // already offset by c
-    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (LINE * C); }
-};
-template <int RB, int LINE> struct RowAcc {
-    static constexpr int STRIDE = 1;
-    Cx<float>* base;   // already offset by the row
-    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (RB * LINE); }
-};
-
 // L2 prefetch of one 32-byte sector (the data of a tile that a later CTA will load)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // CTAs resident at a time (2 per SM on 148 SMs): the tile that far ahead is the one whose loads

@@ -8,8 +8,11 @@
 // (nf, n_traces) complex64 layout the POCS kernels consume.  The inverse does the mirror
 // image (phase, Hermitian symmetrisation = "take the real part", packed complex IFFT).
 #include "p3d_host.h"
+#include "p3d_fft_reg.cuh"
+#include "p3d_pocs_spec.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 using namespace p3d;
@@ -133,6 +136,159 @@ __global__ void k_time_inv(const __grid_constant__ TimeGeom G, const __grid_cons
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// register-resident versions for the usual record lengths (same plans as the POCS column kernel):
+// thread (c, j) holds samples j + e*T of the packed trace pair c.  Requires an even number of
+// traces (8-byte loads of a trace pair, 16-byte stores of its two spectra).
+// ------------------------------------------------------------------------------------------------
+template <typename LP, int C>
+__global__ void __launch_bounds__(LP::T* C, 1)
+k_time_fwd_spec(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict__ tw, const float* __restrict__ x,
+                Cx<float>* __restrict__ F, const Cx<float>* __restrict__ phase) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    const long long tr = (long long)blockIdx.x * 2 * C + 2 * c;          // first trace of this pair
+    const bool ok = tr < G.ntr;                                          // ntr is even: the pair is complete
+    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int n = j + e * T;
+        v[e] = cmake<float>(0.f, 0.f);
+        if (ok && n < G.nt) {
+            const float2 p = *reinterpret_cast<const float2*>(x + (long long)n * G.ntr + tr);
+            v[e] = cmake<float>(p.x, p.y);
+        }
+    }
+    LP::template fft<-1, 0, float>(v, acc, j, tw);
+
+    // one more exchange: Z[N-k] lives in another thread
+    Cx<float>* buf = acc.line(LP::NEXCH & 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) buf[(j + e * T) * C] = v[e];
+    __syncthreads();
+    if (!ok) return;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = j + e * T;
+        if (k < G.nf) {
+            const int km = (N - k) & (N - 1);
+            const Cx<float> z1 = v[e], z2 = buf[km * C];
+            const Cx<float> xa = cmake<float>(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+            const Cx<float> xb = cmake<float>(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+            const Cx<float> ph = phase[k];
+            const Cx<float> fa = cmul(xa, ph), fb = cmul(xb, ph);
+            *reinterpret_cast<float4*>(F + (long long)k * G.ntr + tr) = make_float4(fa.x, fa.y, fb.x, fb.y);
+        }
+    }
+}
+
+template <typename LP, int C>
+__global__ void __launch_bounds__(LP::T* C, 1)
+k_time_inv_spec(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict__ tw, const Cx<float>* __restrict__ F,
+                float* __restrict__ x, const Cx<float>* __restrict__ phase) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    constexpr int half = N / 2;
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    const long long tr = (long long)blockIdx.x * 2 * C + 2 * c;
+    const bool ok = tr < G.ntr;
+    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    Cx<float>* bufA = acc.line(0);
+    Cx<float>* bufB = acc.line(1);
+
+    // stage G_a * phase and G_b * phase by FFT bin (both buffers, natural order)
+    Cx<float> ga[E], gb[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = j + e * T;
+        ga[e] = cmake<float>(0.f, 0.f); gb[e] = cmake<float>(0.f, 0.f);
+        const bool have = G.compute_real ? (k <= half) : true;
+        if (ok && have) {
+            long long row = k;
+            if (!G.compute_real && G.ascending) row = (k + half) & (N - 1);
+            const float4 p = *reinterpret_cast<const float4*>(F + row * G.ntr + tr);
+            const Cx<float> ph = phase[k];
+            ga[e] = cmul(cmake<float>(p.x, p.y), ph);
+            gb[e] = cmul(cmake<float>(p.z, p.w), ph);
+        }
+        bufA[k * C] = ga[e];
+        bufB[k * C] = gb[e];
+    }
+    __syncthreads();
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = j + e * T;
+        const int km = (N - k) & (N - 1);
+        const Cx<float> a2 = bufA[km * C], b2 = bufB[km * C];
+        Cx<float> ha, hb;
+        if (G.compute_real) {
+            if (k <= half) { ha = ga[e]; hb = gb[e]; if (k == 0 || k == half) { ha.y = 0.f; hb.y = 0.f; } }
+            else           { ha = cmake<float>(a2.x, -a2.y); hb = cmake<float>(b2.x, -b2.y); }
+        } else {
+            ha = cmake<float>(0.5f * (ga[e].x + a2.x), 0.5f * (ga[e].y - a2.y));
+            hb = cmake<float>(0.5f * (gb[e].x + b2.x), 0.5f * (gb[e].y - b2.y));
+        }
+        v[e] = cmake<float>(ha.x - hb.y, ha.y + hb.x);          // H[k] = ha + i hb
+    }
+    __syncthreads();                                             // the transform reuses both buffers
+    LP::template fft<+1, 0, float>(v, acc, j, tw);
+    if (!ok) return;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int n = j + e * T;
+        if (n < G.nt) *reinterpret_cast<float2*>(x + (long long)n * G.ntr + tr) = make_float2(v[e].x, v[e].y);
+    }
+}
+
+typedef LinePlan<512, 16, 16, 16, 2> TP512;
+typedef LinePlan<1024, 16, 16, 16, 4> TP1024;
+typedef LinePlan<2048, 16, 16, 16, 8> TP2048;
+typedef LinePlan<4096, 16, 16, 16, 16> TP4096;
+
+template <typename LP, int C>
+bool launch_time_spec(const TimeGeom& G0, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<float>);
+    if (smem > smem_optin - 1024) return false;
+    std::vector<int> rad(LP::NPASS);
+    LP::radices(rad.data());
+    std::vector<Cx<float>> t = spec_twiddle_table(rad);
+    Cx<float>* d_tw = nullptr;
+    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
+    struct Free { Cx<float>* p; ~Free() { cudaFree(p); } } fr{d_tw};
+    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    TimeGeom G = G0; G.C = C;
+    const long long tiles = (G.ntr + 2 * C - 1) / (2 * C);
+    if (!inverse) {
+        P3D_CUDA(cudaFuncSetAttribute(k_time_fwd_spec<LP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_time_fwd_spec<LP, C><<<(unsigned)tiles, LP::T * C, smem>>>(G, d_tw, (const float*)din, (Cx<float>*)dout, d_ph);
+    } else {
+        P3D_CUDA(cudaFuncSetAttribute(k_time_inv_spec<LP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_time_inv_spec<LP, C><<<(unsigned)tiles, LP::T * C, smem>>>(G, d_tw, (const Cx<float>*)din, (float*)dout, d_ph);
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaDeviceSynchronize());
+    return true;
+}
+
+bool try_time_spec(const TimeGeom& G, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
+    if (G.ntr % 2 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
+    switch (G.nfft) {
+        case 512:  return launch_time_spec<TP512, 16>(G, din, dout, d_ph, inverse, smem_optin);
+        case 1024: return launch_time_spec<TP1024, 8>(G, din, dout, d_ph, inverse, smem_optin);
+        case 2048: return launch_time_spec<TP2048, 4>(G, din, dout, d_ph, inverse, smem_optin);
+        case 4096: return launch_time_spec<TP4096, 2>(G, din, dout, d_ph, inverse, smem_optin);
+        default: return false;
+    }
+}
+
 struct DeviceGuard {
     int prev = 0;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
@@ -192,7 +348,10 @@ int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int6
     const long long tiles = (ntr + 2 * C - 1) / (2 * C);
     P3D_REQUIRE(tiles < 2147483647LL, P3D_ERR_BAD_ARG, "too many traces");
     const int threads = 512;
-    if (!inverse) {
+    static const bool no_spec = getenv("P3D_TIME_GENERIC") != nullptr;
+    if (!no_spec && try_time_spec(G, din, dout, d_ph, inverse, prop.sharedMemPerBlockOptin)) {
+        // done by the register-resident kernels
+    } else if (!inverse) {
         P3D_CUDA(cudaFuncSetAttribute(k_time_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
         k_time_fwd<<<(unsigned)tiles, threads, smem>>>(G, ax.dev(), (const float*)din, (Cx<float>*)dout, d_ph);
     } else {
