@@ -117,6 +117,10 @@ int p3d_time_ifft(int device, const void* x, int x_mem, float* out, int out_mem,
                   int64_t nfft, int64_t nt_out, int64_t n_traces, double dt, double t0,
                   int compute_real, int ascending);
 
+/* Device time (CUDA events) spent in the kernels of this thread's last p3d_time_fft / p3d_time_ifft
+ * call (0 when the call used the generic direct kernels). */
+int p3d_time_last_kernel_ms(double* ms);
+
 /* Pinned host memory for asynchronous copies. */
 int p3d_host_alloc(void** ptr, int64_t bytes);
 int p3d_host_free(void* ptr);

@@ -11,6 +11,7 @@
 #include "p3d_fft_reg.cuh"
 #include "p3d_pocs_spec.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -252,6 +253,203 @@ typedef LinePlan<1024, 16, 16, 16, 4> TP1024;
 typedef LinePlan<2048, 16, 16, 16, 8> TP2048;
 typedef LinePlan<4096, 16, 16, 16, 16> TP4096;
 
+// ------------------------------------------------------------------------------------------------
+// Transposing pipeline (the default for the record lengths above).  The time axis is the slowest
+// axis, so a direct kernel makes the whole GPU stream nt different rows at once, 32-64 bytes per
+// row and CTA: on B200 that reaches 0.13-0.45 TB/s (cuFFT on the same layout: 0.39 TB/s).  Instead
+// a chunk of traces is (1) transposed to trace-major with a tiled transpose that streams a few
+// dozen rows at a time, (2) transformed along the now contiguous axis with the register-resident
+// FFT (two real traces per complex line), (3) transposed back into the slice-major spectrum.  The
+// chunk is sized so that both intermediates stay in the 126 MB L2.
+// ------------------------------------------------------------------------------------------------
+// out[c][r] = in[r][c]; 32 x 32 tiles, 32 x 8 threads.  ROWS_FAST: consecutive CTAs walk along the
+// rows of `in` (else along its columns) -- always chosen so that consecutive CTAs walk along the
+// TRACE axis and the GPU streams only a few dozen long time/frequency rows of the cube at a time.
+template <typename T, bool ROWS_FAST>
+__global__ void k_transpose(const T* __restrict__ in, T* __restrict__ out, long long rows, long long cols,
+                            long long in_ld, long long out_ld) {
+    __shared__ T tile[32][33];
+    const long long c0 = (long long)(ROWS_FAST ? blockIdx.y : blockIdx.x) * 32;
+    const long long r0 = (long long)(ROWS_FAST ? blockIdx.x : blockIdx.y) * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const long long r = r0 + ty + i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + i][tx] = in[r * in_ld + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const long long c = c0 + ty + i, r = r0 + tx;
+        if (c < cols && r < rows) out[c * out_ld + r] = tile[tx][ty + i];
+    }
+}
+
+// trace-major forward: xt (ntr_chunk, nt) float -> Ft (ntr_chunk, nf) complex; RB trace PAIRS per CTA
+template <typename LP, int RB>
+__global__ void __launch_bounds__(LP::T* RB, 2)
+k_time_fwd_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict__ tw, const float* __restrict__ xt,
+                Cx<float>* __restrict__ Ft, const Cx<float>* __restrict__ phase, const long long ntr_chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    const int tid = threadIdx.x;
+    const int j = tid % T, rr = tid / T;
+    const long long ta = ((long long)blockIdx.x * RB + rr) * 2, tb = ta + 1;
+    const bool oka = ta < ntr_chunk, okb = tb < ntr_chunk;
+    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    const float* __restrict__ pa = xt + ta * G.nt + j;
+    const float* __restrict__ pb = xt + tb * G.nt + j;
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int n = e * T;
+        const bool in = j + n < G.nt;
+        v[e] = cmake<float>((oka && in) ? pa[n] : 0.f, (okb && in) ? pb[n] : 0.f);
+    }
+    LP::template fft<-1, 0, float>(v, acc, j, tw);
+    Cx<float>* buf = acc.line(LP::NEXCH & 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) buf[j + e * T] = v[e];
+    __syncthreads();
+    Cx<float>* __restrict__ oa = Ft + ta * G.nf;
+    Cx<float>* __restrict__ ob = Ft + tb * G.nf;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = j + e * T;
+        if (k < G.nf) {
+            const Cx<float> z1 = v[e], z2 = buf[(N - k) & (N - 1)];
+            const Cx<float> xa = cmake<float>(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+            const Cx<float> xb = cmake<float>(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+            const Cx<float> ph = phase[k];
+            if (oka) oa[k] = cmul(xa, ph);
+            if (okb) ob[k] = cmul(xb, ph);
+        }
+    }
+}
+
+// trace-major inverse: Ft (ntr_chunk, nf) complex (rows already in FFT-bin order k = 0..nbins-1) -> xt (ntr_chunk, nt)
+template <typename LP, int RB>
+__global__ void __launch_bounds__(LP::T* RB, 2)
+k_time_inv_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict__ tw, const Cx<float>* __restrict__ Ft,
+                float* __restrict__ xt, const Cx<float>* __restrict__ phase, const long long ntr_chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    constexpr int half = N / 2;
+    const int tid = threadIdx.x;
+    const int j = tid % T, rr = tid / T;
+    const long long ta = ((long long)blockIdx.x * RB + rr) * 2, tb = ta + 1;
+    const bool oka = ta < ntr_chunk, okb = tb < ntr_chunk;
+    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    Cx<float>* bufA = acc.line(0);
+    Cx<float>* bufB = acc.line(1);
+    const Cx<float>* __restrict__ ia = Ft + ta * G.nf;
+    const Cx<float>* __restrict__ ib = Ft + tb * G.nf;
+    Cx<float> ga[E], gb[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = j + e * T;
+        ga[e] = cmake<float>(0.f, 0.f); gb[e] = cmake<float>(0.f, 0.f);
+        const bool have = G.compute_real ? (k <= half) : true;
+        if (have) {
+            int row = k;
+            if (!G.compute_real && G.ascending) row = (k + half) & (N - 1);
+            const Cx<float> ph = phase[k];
+            if (oka) ga[e] = cmul(ia[row], ph);
+            if (okb) gb[e] = cmul(ib[row], ph);
+        }
+        bufA[k] = ga[e];
+        bufB[k] = gb[e];
+    }
+    __syncthreads();
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = j + e * T;
+        const int km = (N - k) & (N - 1);
+        const Cx<float> a2 = bufA[km], b2 = bufB[km];
+        Cx<float> ha, hb;
+        if (G.compute_real) {
+            if (k <= half) { ha = ga[e]; hb = gb[e]; if (k == 0 || k == half) { ha.y = 0.f; hb.y = 0.f; } }
+            else           { ha = cmake<float>(a2.x, -a2.y); hb = cmake<float>(b2.x, -b2.y); }
+        } else {
+            ha = cmake<float>(0.5f * (ga[e].x + a2.x), 0.5f * (ga[e].y - a2.y));
+            hb = cmake<float>(0.5f * (gb[e].x + b2.x), 0.5f * (gb[e].y - b2.y));
+        }
+        v[e] = cmake<float>(ha.x - hb.y, ha.y + hb.x);
+    }
+    __syncthreads();
+    LP::template fft<+1, 0, float>(v, acc, j, tw);
+    float* __restrict__ oa = xt + ta * G.nt + j;
+    float* __restrict__ ob = xt + tb * G.nt + j;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int n = e * T;
+        if (j + n < G.nt) { if (oka) oa[n] = v[e].x; if (okb) ob[n] = v[e].y; }
+    }
+}
+
+// device time of the kernels of the last p3d_time_fft / p3d_time_ifft call of this thread
+static thread_local double g_last_kernel_ms = 0.0;
+
+// grow-only scratch kept between calls (per device): the two L2-sized intermediates
+struct TimeScratch { int device = -1; float* tmp_t = nullptr; size_t n_t = 0; Cx<float>* tmp_f = nullptr; size_t n_f = 0; };
+static TimeScratch g_scratch[16];
+static void scratch_get(int device, size_t n_t, size_t n_f, float** tt, Cx<float>** tf) {
+    TimeScratch& S = g_scratch[device & 15];
+    if (S.n_t < n_t) { if (S.tmp_t) cudaFree(S.tmp_t); S.tmp_t = nullptr; S.n_t = 0; P3D_CUDA(cudaMalloc(&S.tmp_t, sizeof(float) * n_t)); S.n_t = n_t; }
+    if (S.n_f < n_f) { if (S.tmp_f) cudaFree(S.tmp_f); S.tmp_f = nullptr; S.n_f = 0; P3D_CUDA(cudaMalloc(&S.tmp_f, sizeof(Cx<float>) * n_f)); S.n_f = n_f; }
+    *tt = S.tmp_t; *tf = S.tmp_f;
+}
+
+template <typename LP, int RB>
+bool launch_time_pipeline(const TimeGeom& G, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
+    if (smem > smem_optin - 1024) return false;
+    std::vector<int> rad(LP::NPASS);
+    LP::radices(rad.data());
+    std::vector<Cx<float>> t = spec_twiddle_table(rad);
+    // chunk of traces whose two intermediates (nt floats + nf complex per trace) stay L2 resident
+    const size_t per_trace = (size_t)G.nt * sizeof(float) + (size_t)G.nf * sizeof(Cx<float>);
+    long long chunk = (long long)((size_t)72 * 1024 * 1024 / per_trace);
+    chunk = std::max<long long>(256, (chunk / 64) * 64);
+    chunk = std::min<long long>(chunk, ((G.ntr + 1) / 2) * 2);
+    Cx<float>* d_tw = nullptr; float* tmp_t = nullptr; Cx<float>* tmp_f = nullptr;
+    struct Free { void* p; cudaEvent_t e0, e1; ~Free() { if (p) cudaFree(p); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); } } fr{nullptr, nullptr, nullptr};
+    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size())); fr.p = d_tw;
+    int dev = 0; P3D_CUDA(cudaGetDevice(&dev));
+    scratch_get(dev, (size_t)G.nt * chunk, (size_t)G.nf * chunk, &tmp_t, &tmp_f);
+    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    P3D_CUDA(cudaEventCreate(&fr.e0)); P3D_CUDA(cudaEventCreate(&fr.e1));
+    P3D_CUDA(cudaEventRecord(fr.e0, 0));
+    P3D_CUDA(cudaFuncSetAttribute(k_time_fwd_rows<LP, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P3D_CUDA(cudaFuncSetAttribute(k_time_inv_rows<LP, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 tb(32, 8);
+    for (long long c0 = 0; c0 < G.ntr; c0 += chunk) {
+        const long long nc = std::min<long long>(chunk, G.ntr - c0);
+        const unsigned ctas = (unsigned)((nc + 2 * RB - 1) / (2 * RB));
+        if (!inverse) {
+            const float* x = (const float*)din + c0;
+            Cx<float>* F = (Cx<float>*)dout + c0;
+            // (nt x nc) -> (nc x nt): columns of `in` are traces -> columns fast
+            k_transpose<float, false><<<dim3((unsigned)((nc + 31) / 32), (unsigned)((G.nt + 31) / 32)), tb>>>(x, tmp_t, G.nt, nc, G.ntr, G.nt);
+            k_time_fwd_rows<LP, RB><<<ctas, LP::T * RB, smem>>>(G, d_tw, tmp_t, tmp_f, d_ph, nc);
+            // (nc x nf) -> (nf x nc): rows of `in` are traces -> rows fast
+            k_transpose<Cx<float>, true><<<dim3((unsigned)((nc + 31) / 32), (unsigned)((G.nf + 31) / 32)), tb>>>(tmp_f, F, nc, G.nf, G.nf, G.ntr);
+        } else {
+            const Cx<float>* F = (const Cx<float>*)din + c0;
+            float* x = (float*)dout + c0;
+            k_transpose<Cx<float>, false><<<dim3((unsigned)((nc + 31) / 32), (unsigned)((G.nf + 31) / 32)), tb>>>(F, tmp_f, G.nf, nc, G.ntr, G.nf);
+            k_time_inv_rows<LP, RB><<<ctas, LP::T * RB, smem>>>(G, d_tw, tmp_f, tmp_t, d_ph, nc);
+            k_transpose<float, true><<<dim3((unsigned)((nc + 31) / 32), (unsigned)((G.nt + 31) / 32)), tb>>>(tmp_t, x, nc, G.nt, G.nt, G.ntr);
+        }
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaEventRecord(fr.e1, 0));
+    P3D_CUDA(cudaDeviceSynchronize());
+    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.e0, fr.e1); g_last_kernel_ms = ms; }
+    return true;
+}
+
 template <typename LP, int C>
 bool launch_time_spec(const TimeGeom& G0, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
     constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<float>);
@@ -278,6 +476,16 @@ bool launch_time_spec(const TimeGeom& G0, const void* din, void* dout, const Cx<
 }
 
 bool try_time_spec(const TimeGeom& G, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
+    static const bool direct = getenv("P3D_TIME_DIRECT") != nullptr;
+    if (!direct) {
+        switch (G.nfft) {
+            case 512:  return launch_time_pipeline<TP512, 4>(G, din, dout, d_ph, inverse, smem_optin);
+            case 1024: return launch_time_pipeline<TP1024, 4>(G, din, dout, d_ph, inverse, smem_optin);
+            case 2048: return launch_time_pipeline<TP2048, 2>(G, din, dout, d_ph, inverse, smem_optin);
+            case 4096: return launch_time_pipeline<TP4096, 1>(G, din, dout, d_ph, inverse, smem_optin);
+            default: return false;
+        }
+    }
     if (G.ntr % 2 != 0) return false;
     if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
     switch (G.nfft) {
@@ -311,14 +519,23 @@ int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int6
     int ndev = 0; P3D_CUDA(cudaGetDeviceCount(&ndev));
     P3D_REQUIRE(device >= 0 && device < ndev, P3D_ERR_BAD_ARG, "device %d out of range", device);
     DeviceGuard guard(device);
-    cudaDeviceProp prop; P3D_CUDA(cudaGetDeviceProperties(&prop, device));
+    struct { size_t sharedMemPerBlockOptin; } prop;
+    { int v = 0; P3D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)); prop.sharedMemPerBlockOptin = (size_t)v; }
+    g_last_kernel_ms = 0.0;
 
+    // the generic direct kernels need an axis plan; the register-resident pipeline (record lengths
+    // 512 .. 4096) does not, so it is only built when that path declines
+    static const bool no_spec = getenv("P3D_TIME_GENERIC") != nullptr;
+    const bool spec_len = !no_spec && (nfft == 512 || nfft == 1024 || nfft == 2048 || nfft == 4096);
     AxisPlan ax;
     struct Cleanup { AxisPlan* a; void* p[3]; ~Cleanup() { a->release(); for (void* q : p) if (q) cudaFree(q); } } cl{&ax, {nullptr, nullptr, nullptr}};
-    ax.build((int)nfft);
-    const int C = choose_cols(ax.L, prop.sharedMemPerBlockOptin);
-    const size_t smem = (size_t)2 * ax.L * C * sizeof(Cx<float>);
-    P3D_REQUIRE(smem <= prop.sharedMemPerBlockOptin, P3D_ERR_NOT_IMPLEMENTED, "time axis of %lld samples does not fit in shared memory", (long long)nfft);
+    int C = 1; size_t smem = 0;
+    if (!spec_len) {
+        ax.build((int)nfft);
+        C = choose_cols(ax.L, prop.sharedMemPerBlockOptin);
+        smem = (size_t)2 * ax.L * C * sizeof(Cx<float>);
+        P3D_REQUIRE(smem <= prop.sharedMemPerBlockOptin, P3D_ERR_NOT_IMPLEMENTED, "time axis of %lld samples does not fit in shared memory", (long long)nfft);
+    }
 
     const int64_t nf = compute_real ? nfft / 2 + 1 : nfft;
     // phase table in double: forward dt*exp(-2 pi i f t0)*window ; inverse exp(+2 pi i f t0)/(dt*nfft)
@@ -348,15 +565,22 @@ int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int6
     const long long tiles = (ntr + 2 * C - 1) / (2 * C);
     P3D_REQUIRE(tiles < 2147483647LL, P3D_ERR_BAD_ARG, "too many traces");
     const int threads = 512;
-    static const bool no_spec = getenv("P3D_TIME_GENERIC") != nullptr;
-    if (!no_spec && try_time_spec(G, din, dout, d_ph, inverse, prop.sharedMemPerBlockOptin)) {
+    bool done = spec_len && try_time_spec(G, din, dout, d_ph, inverse, prop.sharedMemPerBlockOptin);
+    if (!done && spec_len) {          // the pipeline declined (e.g. shared memory): fall back to the direct kernels
+        ax.build((int)nfft);
+        C = choose_cols(ax.L, prop.sharedMemPerBlockOptin);
+        smem = (size_t)2 * ax.L * C * sizeof(Cx<float>);
+        G.C = C;
+    }
+    const long long tiles2 = (ntr + 2 * C - 1) / (2 * C);
+    if (done) {
         // done by the register-resident kernels
     } else if (!inverse) {
         P3D_CUDA(cudaFuncSetAttribute(k_time_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
-        k_time_fwd<<<(unsigned)tiles, threads, smem>>>(G, ax.dev(), (const float*)din, (Cx<float>*)dout, d_ph);
+        k_time_fwd<<<(unsigned)tiles2, threads, smem>>>(G, ax.dev(), (const float*)din, (Cx<float>*)dout, d_ph);
     } else {
         P3D_CUDA(cudaFuncSetAttribute(k_time_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
-        k_time_inv<<<(unsigned)tiles, threads, smem>>>(G, ax.dev(), (const Cx<float>*)din, (float*)dout, d_ph);
+        k_time_inv<<<(unsigned)tiles2, threads, smem>>>(G, ax.dev(), (const Cx<float>*)din, (float*)dout, d_ph);
     }
     P3D_CUDA(cudaGetLastError());
     P3D_CUDA(cudaDeviceSynchronize());
@@ -367,6 +591,8 @@ int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int6
 }  // namespace
 
 extern "C" {
+
+int p3d_time_last_kernel_ms(double* ms) { if (!ms) return P3D_ERR_BAD_ARG; *ms = g_last_kernel_ms; return P3D_OK; }
 
 int p3d_time_fft(int device, const float* x, int x_mem, void* out, int out_mem, int64_t nt, int64_t nfft,
                  int64_t n_traces, double dt, double t0, int compute_real, const double* window) {

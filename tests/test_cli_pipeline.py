@@ -107,3 +107,26 @@ def test_steps_12_13_14_chain_matches_oracle(tmp_path, compute_real):
     # the interpolation actually helps: closer to the dense cube than the sparse input is
     sparse = cube.data("env")
     assert np.linalg.norm(x - dense) < 0.8 * np.linalg.norm(sparse - dense)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nt,compute_real", [(64, True), (64, False), (512, True), (2048, True)])
+def test_on_device_chain_matches_oracle_chain(nt, compute_real):
+    """12 -> 13 -> 14 chained on the device (pipeline.interpolate_time_cube) against the oracle
+    chain time_fft -> pocs_cube -> time_ifft; nt = 512 / 2048 exercise the register-resident
+    transposing time-axis kernels, nt = 64 the generic ones."""
+    from oracle import pocs_oracle as orc, time_axis_oracle as tor
+    from pseudo_3d_interpolation_b200 import pipeline
+    n1, n2 = (20, 18) if nt >= 512 else (24, 20)
+    cube, dense = _time_cube(nt=nt, n1=n1, n2=n2, seed=8)
+    x, twt, fold = cube.data("env"), cube.coords["twt"], cube.data("fold")
+    params = dict(niter=12, thresh_op="soft", thresh_model="linear", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-2)
+    res = {}
+    y, spec = pipeline.interpolate_time_cube(x, twt, fold, compute_real=compute_real, return_spectrum=True, results=res, **params)
+    F_ref, f = tor.time_fft(x, twt, compute_real=compute_real)
+    S_ref = orc.pocs_cube(F_ref, fold, **params)
+    x_ref = tor.time_ifft(S_ref, synth.DT_MS, synth.T0_MS, compute_real=compute_real, ascending=False)
+    assert y.shape == x_ref.shape and y.dtype == np.float32
+    assert np.linalg.norm(spec - S_ref) / np.linalg.norm(S_ref) < 1e-4
+    assert np.linalg.norm(y - x_ref) / np.linalg.norm(x_ref) < 1e-4
+    assert np.all(res["niterations"][np.abs(F_ref).reshape(F_ref.shape[0], -1).max(axis=1) > 0] == 12)

@@ -47,7 +47,8 @@ def main():
             fn()
         lib.p3d_device_synchronize(0)
         el = (time.perf_counter() - t) / reps
-        print(f"{name}: nt={nt} traces={ntr} real={real}: {el*1e3:.2f} ms, {nbytes/el/1e9:.0f} GB/s algorithmic ({nbytes/1e9:.1f} GB moved)")
+        kms = C.c_double(); lib.p3d_time_last_kernel_ms(C.byref(kms))
+        print(f"{name}: nt={nt} traces={ntr} real={real}: call {el*1e3:.2f} ms; kernels {kms.value:.2f} ms = {nbytes/max(kms.value,1e-9)/1e6:.0f} GB/s algorithmic ({nbytes/1e9:.1f} GB)")
     y = np.empty((nt, 64), np.float32)
     full = np.empty_like(x); dy.download(full)
     err = np.linalg.norm(full[:, :4096] - x[:, :4096]) / np.linalg.norm(x[:, :4096])
