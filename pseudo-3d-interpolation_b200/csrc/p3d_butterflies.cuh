@@ -28,6 +28,49 @@ template <typename T> __host__ __device__ __forceinline__ Cx<T> cscale(Cx<T> a, 
 template <int DIR, typename T> __host__ __device__ __forceinline__ Cx<T> cmul_i(Cx<T> a) {
     return DIR < 0 ? cmake<T>(a.y, -a.x) : cmake<T>(-a.y, a.x);
 }
+// c + s * a  (real scalar s times complex a)
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cfma_real(T s, Cx<T> a, Cx<T> c) {
+    return cmake<T>(c.x + s * a.x, c.y + s * a.y);
+}
+// s * a
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cmul_real(T s, Cx<T> a) { return cmake<T>(s * a.x, s * a.y); }
+
+// ---------------------------------------------------------------------------------------
+// Blackwell packed FP32: add/mul/fma.f32x2 execute both halves of a 64-bit register pair in one
+// instruction (SASS FADD2 / FMUL2 / FFMA2, with free per-operand swap, broadcast and sign
+// modifiers).  A complex64 value IS such a pair, so complex add/sub, real-scalar FMA and the
+// complex multiply map to one or two packed instructions instead of two or four scalar ones;
+// on sm_100 a scalar 3-register FFMA issues at half the FP32 rate, the packed forms at full rate.
+// These overloads are picked for Cx<float> in device code; double and host code use the
+// templates above.
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(P3D_NO_F32X2)
+__device__ __forceinline__ unsigned long long cx_bits(Cx<float> a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ Cx<float> cx_from(unsigned long long u) { return *reinterpret_cast<Cx<float>*>(&u); }
+__device__ __forceinline__ Cx<float> add2(Cx<float> a, Cx<float> b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b))); return cx_from(r);
+}
+__device__ __forceinline__ Cx<float> sub2(Cx<float> a, Cx<float> b) {
+    unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b))); return cx_from(r);
+}
+__device__ __forceinline__ Cx<float> mul2(Cx<float> a, Cx<float> b) {
+    unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b))); return cx_from(r);
+}
+__device__ __forceinline__ Cx<float> fma2(Cx<float> a, Cx<float> b, Cx<float> c) {
+    unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)), "l"(cx_bits(c))); return cx_from(r);
+}
+__device__ __forceinline__ Cx<float> cadd(Cx<float> a, Cx<float> b) { return add2(a, b); }
+__device__ __forceinline__ Cx<float> csub(Cx<float> a, Cx<float> b) { return sub2(a, b); }
+__device__ __forceinline__ Cx<float> cmul(Cx<float> a, Cx<float> w) {
+    return fma2(cmake<float>(a.x, a.x), w, mul2(cmake<float>(a.y, a.y), cmake<float>(-w.y, w.x)));
+}
+__device__ __forceinline__ Cx<float> cmulc(Cx<float> a, Cx<float> w) {
+    return fma2(cmake<float>(a.x, a.x), cmake<float>(w.x, -w.y), mul2(cmake<float>(a.y, a.y), cmake<float>(w.y, w.x)));
+}
+__device__ __forceinline__ Cx<float> cscale(Cx<float> a, float s) { return mul2(a, cmake<float>(s, s)); }
+__device__ __forceinline__ Cx<float> cfma_real(float s, Cx<float> a, Cx<float> c) { return fma2(cmake<float>(s, s), a, c); }
+__device__ __forceinline__ Cx<float> cmul_real(float s, Cx<float> a) { return mul2(cmake<float>(s, s), a); }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // constexpr trigonometry: cos(2 pi m / n), sin(2 pi m / n) for integer m, n
@@ -108,13 +151,13 @@ template <int P, int DIR, typename T> struct BflyPrime {
         v[0] = sum;
 #pragma unroll
         for (int k = 1; k <= H; ++k) {
-            Cx<T> A = x0, B = cmake<T>(T(0), T(0));
+            Cx<T> A = x0, B;
 #pragma unroll
             for (int j = 1; j <= H; ++j) {
                 const T c = (T)cx_cos2pi(j * k, P);
                 const T sn = (T)cx_sin2pi(j * k, P);
-                A.x += c * s[j - 1].x; A.y += c * s[j - 1].y;
-                B.x += sn * d[j - 1].x; B.y += sn * d[j - 1].y;
+                A = cfma_real(c, s[j - 1], A);
+                B = (j == 1) ? cmul_real(sn, d[0]) : cfma_real(sn, d[j - 1], B);
             }
             // forward: X[k] = A - i B, X[P-k] = A + i B ; inverse swaps
             Cx<T> iB = cmul_i<DIR>(B);         // DIR*i*B

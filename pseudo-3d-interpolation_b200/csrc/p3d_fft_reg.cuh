@@ -120,7 +120,7 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
 #pragma unroll
                 for (int r = 0; r < R; ++r) w[(r * Ns) * S] = v[q + r * Q];
             }
-            __syncthreads();
+            acc.sync();
             if constexpr (TT % B == 0) {
                 // hi(pos) = j/B + e*(TT/B)
                 const Cx<T>* rd = line + (j + DELTA * (j / B)) * S;
@@ -159,11 +159,12 @@ template <int C, int LINE> struct ColAcc {
     static constexpr int STRIDE = C;
     Cx<float>* base;   // already offset by c
     __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (LINE * C); }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 template <int RB, int LINE> struct RowAcc {
     static constexpr int STRIDE = 1;
     Cx<float>* base;   // already offset by the row
     __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (RB * LINE); }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
-
 }  // namespace p3d

@@ -229,6 +229,7 @@ std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices) {
 }
 
 typedef LinePlan<1000, 10, 10, 10, 10> LP1000;
+typedef LinePlan<1000, 20, 10, 10, 10> LP1000E20;
 typedef LinePlan<2000, 10, 10, 10, 10, 2> LP2000;
 typedef LinePlan<256, 16, 16, 16> LP256;
 typedef LinePlan<200, 20, 10, 20> LP200;
@@ -243,6 +244,8 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
         case 1000:
             if (variant == 1) P3D_COLS(LP1000, 8, 1, "spec<1000,E10,10x10x10,C8,1cta>");
             else if (variant == 6) P3D_COLS(LP1000, 4, 3, "spec<1000,E10,10x10x10,C4,3cta>");
+            else if (variant == 7) P3D_COLS(LP1000E20, 4, 2, "spec<1000,E20,10x10x10,C4,2cta>");
+            else if (variant == 8) P3D_COLS(LP1000E20, 8, 1, "spec<1000,E20,10x10x10,C8,1cta>");
             else if (variant == 2) { k.cols_iter = launch_cols<LP1000, 4, 2, true>; k.cols_name = "spec<1000,E10,10x10x10,C4,2cta,l2prefetch>"; k.cols_radices = radices_of<LP1000>(); }
             else if (variant == 4) P3D_COLS(LP1000, 2, 4, "spec<1000,E10,10x10x10,C2,4cta>");
             else              P3D_COLS(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta>");
