@@ -394,3 +394,27 @@ def test_time_axis_window(p3d):
         F, _ = timeaxis.time_fft(x, twt, compute_real=True, window=w)
         Fr, _ = tor.time_fft(x, twt, compute_real=True, window=wr)
         assert rel_l2(F, Fr) < 5e-6
+
+
+@pytest.mark.parametrize("nt,shape,real,up", [(512, (9, 7), True, 1), (512, (9, 7), False, 1), (256, (5, 11), True, 2),
+                                              (1024, (6, 5), True, 1), (2048, (3, 5), False, 1), (4096, (2, 3), True, 1),
+                                              (300, (4, 5), True, 1), (1201, (2, 2), False, 1)])
+def test_time_axis_register_pipeline_sizes(nt, shape, real, up, p3d):
+    """record lengths served by the transposing register-resident pipeline (512..4096, here with
+    odd trace counts and zero padding) and generic / Bluestein lengths, vs the numpy oracle."""
+    from oracle import time_axis_oracle as tor
+    from pseudo_3d_interpolation_b200 import timeaxis, synth
+    rng = np.random.default_rng(nt)
+    x = rng.standard_normal((nt,) + shape).astype(np.float32)
+    twt = synth.T0_MS + synth.DT_MS * np.arange(nt)
+    F, f = timeaxis.time_fft(x, twt, compute_real=real, upsampling_factor=up)
+    Fr, fr = tor.time_fft(x, twt, compute_real=real, upsampling_factor=up)
+    assert F.shape == Fr.shape and rel_l2(F, Fr) < 5e-6
+    nte = nt - (nt % 2)
+    Fin = np.fft.fftshift(F, axes=0) if not real else F
+    xb = timeaxis.time_ifft(Fin, synth.DT_MS / 1.0, synth.T0_MS, compute_real=real, ascending=True, nt_out=nte)
+    if up == 1:
+        assert rel_l2(xb, x[:nte]) < 5e-6
+    else:
+        xr = tor.time_ifft(np.fft.fftshift(Fr, axes=0) if not real else Fr, synth.DT_MS, synth.T0_MS, compute_real=real)
+        assert rel_l2(xb, xr[:nte]) < 5e-6
