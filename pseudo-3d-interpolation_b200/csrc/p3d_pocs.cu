@@ -191,13 +191,15 @@ void install_spec(p3d_plan* P, int variant) {
 // ---- launches -----------------------------------------------------------------------------------
 void launch_rows_init(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices) {
     prof_begin(P, st, 0);
-    generic_rows_init(generic_cfg(P), P->ax2.dev(), A, nslices, st);
+    if (P->spec.rows_init && !P->force_generic) P->spec.rows_init(P->geom, P->spec_tw_rows, A, nslices, st);
+    else generic_rows_init(generic_cfg(P), P->ax2.dev(), A, nslices, st);
     prof_end(P, st);
     P3D_CUDA(cudaGetLastError());
 }
 void launch_cols_stats(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices) {
     prof_begin(P, st, 1);
-    generic_cols_stats(generic_cfg(P), P->ax1.dev(), A, nslices, st);
+    if (P->spec.cols_stats && !P->force_generic) P->spec.cols_stats(P->geom, P->spec_tw_cols, A, nslices, st);
+    else generic_cols_stats(generic_cfg(P), P->ax1.dev(), A, nslices, st);
     prof_end(P, st);
     P3D_CUDA(cudaGetLastError());
 }

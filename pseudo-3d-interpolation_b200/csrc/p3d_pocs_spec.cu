@@ -160,6 +160,110 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     }
 }
 
+// ---- once-per-slice kernels: row FFT of the observed slice, column FFT + schedule statistics -------
+template <typename LP, int RB, int MINB>
+__global__ void __launch_bounds__(LP::T* RB, MINB)
+k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_s[32];
+    __shared__ unsigned long long red_n[32];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    const int s = blockIdx.y;
+    if (A.adaptive && A.stop[s] != 0) return;
+    const int tid = threadIdx.x;
+    const int j = tid % T, rr = tid / T;
+    const int row = blockIdx.x * RB + rr;
+    const bool ok = row < G.n1;
+    const long long off = (long long)s * G.n1 * N + (long long)row * N + j;
+    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    const Cx<float>* __restrict__ Dp = A.D + off;
+    Cx<float>* __restrict__ Wp = A.W + off;
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = ok ? Dp[e * T] : cmake<float>(0.f, 0.f);
+    float part = 0.f;
+    unsigned long long nnz = 0ull;
+    if (!A.adaptive) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            nnz += (v[e].x != 0.f || v[e].y != 0.f) ? 1ull : 0ull;
+            part += sqrtf(v[e].x * v[e].x + v[e].y * v[e].y);
+        }
+    } else {
+        // APOCS prologue with x_old = x (functions/POCS.py:572-575)
+        const long long midx = (A.first_slice + s) / G.slices_per_mask;
+        const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float m = ((mbits >> e) & 1u) ? 1.f : 0.f;
+            const float keep = 1.f - A.alpha * m, om = 1.f - A.alpha;
+            const Cx<float> d = v[e];
+            const Cx<float> xt = cmake<float>(A.alpha * d.x + keep * d.x, A.alpha * d.y + keep * d.y);
+            v[e] = cmake<float>(xt.x + om * (d.x - m * d.x), xt.y + om * (d.y - m * d.y));
+        }
+    }
+    if (A.accum) {
+        double dp = warp_sum((double)part);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
+        if ((tid & 31) == 0) { red_s[tid >> 5] = dp; red_n[tid >> 5] = nnz; }
+        __syncthreads();
+        if (tid < 32) {
+            constexpr int NW = (T * RB + 31) / 32;
+            double t = tid < NW ? red_s[tid] : 0.0;
+            unsigned long long c = tid < NW ? red_n[tid] : 0ull;
+            t = warp_sum(t);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (tid == 0) { atomicAdd(&A.S[(long long)s * (A.niter + 1)], t); atomicAdd(&A.stats[s].nnz, c); }
+        }
+    }
+    LP::template fft<-1, 0, float>(v, acc, j, tw);
+    if (ok) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) Wp[e * T] = v[e];
+    }
+}
+
+template <typename LP, int C, int MINB>
+__global__ void __launch_bounds__(LP::T* C, MINB)
+k_cols_stats_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    const int s = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    const int col = blockIdx.x * C + c;
+    const bool ok = col < G.n2;
+    const Cx<float>* __restrict__ Ws = A.W + (long long)s * N * G.n2 + col;
+    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(j + e * T) * G.n2] : cmake<float>(0.f, 0.f);
+    LP::template fft<-1, 0, float>(v, acc, j, tw);
+    unsigned long long kmax = 0ull; float ssf = 0.f; unsigned int amax = 0u, amin = 0xffffffffu;
+    if (ok) {
+        Cx<float>* __restrict__ X0 = A.OUT + (long long)s * N * G.n2 + col;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const unsigned long long key = lex_key(v[e].x, v[e].y);
+            kmax = key > kmax ? key : kmax;
+            const float r2 = v[e].x * v[e].x + v[e].y * v[e].y;
+            ssf += r2;
+            const unsigned int rb = __float_as_uint(sqrtf(r2));
+            amax = rb > amax ? rb : amax; amin = rb < amin ? rb : amin;
+            if (A.store_x0) X0[(long long)(j + e * T) * G.n2] = v[e];
+        }
+    }
+    kmax = warp_max_u64(kmax); const double ss = warp_sum((double)ssf); amax = warp_max_u32(amax); amin = warp_min_u32(amin);
+    if ((tid & 31) == 0) {
+        atomicMax(&A.stats[s].lexmax_key, kmax);
+        atomicAdd(&A.stats[s].sumsq, ss);
+        atomicMax(&A.stats[s].maxabs_bits, amax);
+        atomicMin(&A.stats[s].minabs_bits, amin);
+    }
+}
+
 // mask bytes -> one word per (mask, row, j): bit e = mask[row][j + e*T] != 0
 template <int T, int E>
 __global__ void k_pack_mask(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits, long long total_rows) {
@@ -196,6 +300,28 @@ static void launch_rows(const PocsGeom& G, const Cx<float>* tw, const BandArgs<f
     }
     dim3 grid((G.n1 + RB - 1) / RB, ns);
     k_rows_spec<LP, RB, MINB, PF><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+}
+template <typename LP, int RB, int MINB>
+static void launch_rows_init(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_rows_init_spec<LP, RB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid((G.n1 + RB - 1) / RB, ns);
+    k_rows_init_spec<LP, RB, MINB><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+}
+template <typename LP, int C, int MINB>
+static void launch_cols_stats(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<float>);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_cols_stats_spec<LP, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid((G.n2 + C - 1) / C, ns);
+    k_cols_stats_spec<LP, C, MINB><<<grid, LP::T * C, smem, st>>>(G, tw, A);
 }
 template <typename LP>
 static void launch_pack(const uint8_t* mask, uint32_t* bits, int n_masks, int n1, cudaStream_t st) {
@@ -234,8 +360,10 @@ typedef LinePlan<2000, 10, 10, 10, 10, 2> LP2000;
 typedef LinePlan<256, 16, 16, 16> LP256;
 typedef LinePlan<200, 20, 10, 20> LP200;
 
-#define P3D_COLS(LP, C, MINB, NAME) do { k.cols_iter = launch_cols<LP, C, MINB>; k.cols_name = NAME; k.cols_radices = radices_of<LP>(); } while (0)
-#define P3D_ROWS(LP, RB, MINB, NAME) do { k.rows_iter = launch_rows<LP, RB, MINB>; k.rows_name = NAME; k.rows_radices = radices_of<LP>(); \
+#define P3D_COLS(LP, C, MINB, NAME) do { k.cols_iter = launch_cols<LP, C, MINB>; k.cols_stats = launch_cols_stats<LP, C, MINB>; \
+                                         k.cols_name = NAME; k.cols_radices = radices_of<LP>(); } while (0)
+#define P3D_ROWS(LP, RB, MINB, NAME) do { k.rows_iter = launch_rows<LP, RB, MINB>; k.rows_init = launch_rows_init<LP, RB, MINB>; \
+                                          k.rows_name = NAME; k.rows_radices = radices_of<LP>(); \
                                           k.pack_mask = launch_pack<LP>; k.rows_T = LP::T; } while (0)
 
 SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
@@ -244,11 +372,11 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
         case 1000:
             if (variant == 1) P3D_COLS(LP1000, 8, 1, "spec<1000,E10,10x10x10,C8,1cta>");
             else if (variant == 6) P3D_COLS(LP1000, 4, 3, "spec<1000,E10,10x10x10,C4,3cta>");
-            else if (variant == 7) P3D_COLS(LP1000E20, 4, 2, "spec<1000,E20,10x10x10,C4,2cta>");
+            else if (variant == 7) P3D_COLS(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta>");
             else if (variant == 8) P3D_COLS(LP1000E20, 8, 1, "spec<1000,E20,10x10x10,C8,1cta>");
             else if (variant == 2) { k.cols_iter = launch_cols<LP1000, 4, 2, true>; k.cols_name = "spec<1000,E10,10x10x10,C4,2cta,l2prefetch>"; k.cols_radices = radices_of<LP1000>(); }
             else if (variant == 4) P3D_COLS(LP1000, 2, 4, "spec<1000,E10,10x10x10,C2,4cta>");
-            else              P3D_COLS(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta>");
+            else              P3D_COLS(LP1000E20, 4, 2, "spec<1000,E20,10x10x10,C4,2cta>");
             break;
         case 2000:
             if (variant == 4) P3D_COLS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,C2,2cta>");
@@ -264,14 +392,23 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else if (variant == 2) { k.rows_iter = launch_rows<LP1000, 4, 2, true>; k.rows_name = "spec<1000,E10,10x10x10,RB4,2cta,l2prefetch>"; k.rows_radices = radices_of<LP1000>(); k.pack_mask = launch_pack<LP1000>; k.rows_T = LP1000::T; }
             else if (variant == 3) P3D_ROWS(LP1000, 4, 2, "spec<1000,E10,10x10x10,RB4,2cta>");
             else if (variant == 5) P3D_ROWS(LP1000, 2, 4, "spec<1000,E10,10x10x10,RB2,4cta>");
-            else              P3D_ROWS(LP1000, 1, 7, "spec<1000,E10,10x10x10,RB1,7cta>");
+            else if (variant == 9) P3D_ROWS(LP1000, 1, 7, "spec<1000,E10,10x10x10,RB1,7cta>");
+            else              P3D_ROWS(LP1000, 1, 8, "spec<1000,E10,10x10x10,RB1,8cta>");
             break;
         case 2000:
             if (variant == 3) P3D_ROWS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,RB4>");
             else              P3D_ROWS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,RB2,2cta>");
             break;
-        case 256:  P3D_ROWS(LP256, 16, 3, "spec<256,E16,16x16,RB16>"); break;
-        case 200:  P3D_ROWS(LP200, 16, 4, "spec<200,E20,10x20,RB16>"); break;
+        case 256:
+            if (variant == 1) P3D_ROWS(LP256, 16, 3, "spec<256,E16,16x16,RB16>");
+            else if (variant == 2) P3D_ROWS(LP256, 4, 10, "spec<256,E16,16x16,RB4>");
+            else P3D_ROWS(LP256, 8, 5, "spec<256,E16,16x16,RB8>");
+            break;
+        case 200:
+            if (variant == 1) P3D_ROWS(LP200, 16, 4, "spec<200,E20,10x20,RB16>");
+            else if (variant == 2) P3D_ROWS(LP200, 6, 8, "spec<200,E20,10x20,RB6>");
+            else P3D_ROWS(LP200, 3, 12, "spec<200,E20,10x20,RB3>");
+            break;
         default: break;
     }
     return k;

@@ -14,6 +14,8 @@ typedef void (*PackMaskLaunch)(const uint8_t* mask, uint32_t* bits, int n_masks,
 struct SpecKernels {
     ColsIterLaunch cols_iter = nullptr;
     RowsIterLaunch rows_iter = nullptr;
+    RowsIterLaunch rows_init = nullptr;   // row FFT of the observed slice (+ nnz, sum|d|, APOCS prologue)
+    RowsIterLaunch cols_stats = nullptr;  // column FFT + schedule statistics (same signature)
     PackMaskLaunch pack_mask = nullptr;
     const char* cols_name = "generic";
     const char* rows_name = "generic";
