@@ -357,6 +357,7 @@ std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices) {
 typedef LinePlan<1000, 10, 10, 10, 10> LP1000;
 typedef LinePlan<1000, 20, 10, 10, 10> LP1000E20;
 typedef LinePlan<2000, 10, 10, 10, 10, 2> LP2000;
+typedef LinePlan<2000, 20, 20, 10, 10> LP2000E20;
 typedef LinePlan<256, 16, 16, 16> LP256;
 typedef LinePlan<200, 20, 10, 20> LP200;
 
@@ -380,7 +381,9 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             break;
         case 2000:
             if (variant == 4) P3D_COLS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,C2,2cta>");
-            else              P3D_COLS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4>");
+            else if (variant == 5) P3D_COLS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4>");
+            else if (variant == 6) P3D_COLS(LP2000E20, 4, 2, "spec<2000,E20,20x10x10,C4,2cta>");
+            else              P3D_COLS(LP2000E20, 4, 1, "spec<2000,E20,20x10x10,C4,1cta>");
             break;
         case 256:  P3D_COLS(LP256, 16, 3, "spec<256,E16,16x16,C16>"); break;
         case 200:  P3D_COLS(LP200, 16, 4, "spec<200,E20,10x20,C16>"); break;
@@ -393,11 +396,15 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else if (variant == 3) P3D_ROWS(LP1000, 4, 2, "spec<1000,E10,10x10x10,RB4,2cta>");
             else if (variant == 5) P3D_ROWS(LP1000, 2, 4, "spec<1000,E10,10x10x10,RB2,4cta>");
             else if (variant == 9) P3D_ROWS(LP1000, 1, 7, "spec<1000,E10,10x10x10,RB1,7cta>");
+            else if (variant == 10) P3D_ROWS(LP1000E20, 2, 4, "spec<1000,E20,10x10x10,RB2,4cta>");
+            else if (variant == 11) P3D_ROWS(LP1000E20, 1, 8, "spec<1000,E20,10x10x10,RB1,8cta>");
             else              P3D_ROWS(LP1000, 1, 8, "spec<1000,E10,10x10x10,RB1,8cta>");
             break;
         case 2000:
             if (variant == 3) P3D_ROWS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,RB4>");
-            else              P3D_ROWS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,RB2,2cta>");
+            else if (variant == 5) P3D_ROWS(LP2000, 1, 4, "spec<2000,E10,10x10x10x2,RB1,4cta>");
+            else if (variant == 6) P3D_ROWS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,RB2,2cta>");
+            else              P3D_ROWS(LP2000E20, 1, 4, "spec<2000,E20,20x10x10,RB1,4cta>");
             break;
         case 256:
             if (variant == 1) P3D_ROWS(LP256, 16, 3, "spec<256,E16,16x16,RB16>");
