@@ -519,7 +519,13 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     // chunk size: everything at once on one lane; with two lanes at least two chunks per lane
     // (copy/compute overlap) but never tiny chunks
     int64_t want = n_slices;
-    if (lanes > 1) want = std::max<int64_t>(std::min<int64_t>(n_slices, 16), (n_slices + 2 * lanes - 1) / (2 * lanes));
+    if (lanes > 1) {
+        // ~4 chunks per lane keep the un-overlapped first H2D / last D2H short; chunks stay large
+        // enough (>= ~48 MB of slices) to fill the GPU
+        const int64_t ne_ = (int64_t)P->n1 * P->n2;
+        const int64_t min_chunk = std::max<int64_t>(1, std::min<int64_t>(n_slices, (int64_t)(48e6 / (8.0 * (double)ne_)) + 1));
+        want = std::max<int64_t>(min_chunk, (n_slices + 4 * lanes - 1) / (4 * lanes));
+    }
     if (P->max_slices > 0) want = std::min<int64_t>(want, P->max_slices);
     int64_t have = 0;
     for (int i = 0; i < lanes; ++i) have = (i == 0) ? P->lanes[i].cap : std::min(have, P->lanes[i].cap);

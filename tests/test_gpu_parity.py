@@ -418,3 +418,70 @@ def test_time_axis_register_pipeline_sizes(nt, shape, real, up, p3d):
     else:
         xr = tor.time_ifft(np.fft.fftshift(Fr, axes=0) if not real else Fr, synth.DT_MS, synth.T0_MS, compute_real=real)
         assert rel_l2(xb, xr[:nte]) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------
+def test_edge_empty_single_and_degenerate_shapes(p3d):
+    plan = p3d.PocsPlan(12, 10)
+    y, info = plan.run(np.zeros((0, 12, 10), np.complex64), np.ones((12, 10), np.uint8), niter=5)
+    assert y.shape == (0, 12, 10) and info["niterations"].shape == (0,)
+    for shape in [(1, 32), (32, 1), (2, 3), (7, 1)]:
+        x, mask = make_input(dict(seed=3, shape=shape, keep=0.6))
+        params = dict(niter=6, thresh_op="soft", thresh_model="linear", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-2)
+        ref = orc.pocs_slice(x.astype(np.complex128), mask, **params)
+        got = p3d.POCS(x, mask, None, transform=np.fft.fft2, itransform=np.fft.ifft2, transform_kind="FFT", **params)
+        assert rel_l2(got, ref) <= RTOL, (shape, rel_l2(got, ref))
+
+
+def test_edge_full_and_empty_masks(p3d):
+    x, _ = make_input(dict(seed=4, shape=(40, 36), keep=1.0))
+    ones = np.ones(x.shape, np.uint8)
+    params = dict(niter=8, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-3)
+    y = p3d.POCS(x, ones, None, transform=np.fft.fft2, itransform=np.fft.ifft2, transform_kind="FFT", **params)
+    assert np.array_equal(y, x)                                  # nothing missing: observed data returned exactly
+    zeros = np.zeros(x.shape, np.uint8)                          # nothing "observed": x is still re-inserted (alpha * x)
+    y0 = p3d.POCS(x, zeros, None, transform=np.fft.fft2, itransform=np.fft.ifft2, transform_kind="FFT", **params)
+    ref0 = orc.pocs_slice(x.astype(np.complex128), zeros, **params)
+    assert rel_l2(y0, ref0) <= RTOL
+
+
+def test_edge_niter_one_and_dtypes(p3d):
+    x, mask = make_input(dict(seed=6, shape=(24, 30), keep=0.5))
+    kw = dict(transform=np.fft.fft2, itransform=np.fft.ifft2, transform_kind="FFT")
+    # niter = 1: (niter - 1) = 0 makes the reference's multiplier 0/0 = nan -> tau = nan -> nothing thresholded
+    with np.errstate(all="ignore"):
+        ref1 = orc.pocs_slice(x.astype(np.complex128), mask, niter=1, thresh_op="hard", thresh_model="linear", eps=0.0)
+    info = {}
+    y1 = p3d.POCS(x, mask, None, niter=1, thresh_op="hard", thresh_model="linear", eps=0.0, results_dict=info, **kw)
+    assert info["niterations"] == 1 and rel_l2(y1, ref1) <= RTOL
+    # complex128 / float64 / Fortran-ordered inputs keep their dtype on return
+    y128 = p3d.POCS(np.asfortranarray(x.astype(np.complex128)), mask, None, niter=5, **kw)
+    assert y128.dtype == np.complex128
+    xr = np.asfortranarray(x.real.astype(np.float64))
+    yr = p3d.POCS(xr, mask, None, niter=5, **kw)
+    assert yr.dtype == np.float64 and not np.iscomplexobj(yr)
+    refr = orc.pocs_slice(xr, mask, niter=5)
+    assert rel_l2(yr, refr) <= RTOL
+
+
+def test_edge_many_small_cubes_with_own_masks_and_early_exit(p3d):
+    """config-5 layout in miniature: a batch of cubes, each with its own mask, default eps."""
+    per, ncubes, shape = 5, 6, (32, 32)
+    xs, masks = [], []
+    for cidx in range(ncubes):
+        x, m = make_input(dict(seed=500 + cidx, shape=shape, keep=0.25 + 0.05 * cidx, nwaves=3))
+        masks.append(m)
+        xs += [x * (1 + 0.2 * s) for s in range(per)]
+    x = np.stack(xs).astype(np.complex64)
+    mask = np.stack(masks)
+    params = dict(niter=40, thresh_op="garrote", thresh_model="exponential", eps=1e-9, alpha=1.0, p_max=0.99, p_min=1e-4)
+    plan = p3d.PocsPlan(*shape, max_slices=7)             # forces several chunks that straddle cube boundaries
+    y, info = plan.run(x, mask, slices_per_mask=per, **params)
+    for i in range(x.shape[0]):
+        oi = {}
+        ref = orc.pocs_slice(x[i].astype(np.complex128), mask[i // per], info=oi, **params)
+        assert abs(int(info["niterations"][i]) - oi["niterations"]) <= 1
+        if int(info["niterations"][i]) == oi["niterations"]:
+            assert rel_l2(y[i], ref) <= RTOL, (i, rel_l2(y[i], ref))
