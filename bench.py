@@ -389,6 +389,44 @@ def main():
         except Exception as ex:          # noqa: BLE001
             diag = {"error": str(ex)[:200]}
 
+    # ---- extras (outside the timed region, small samples): float64 state mode and the time-axis kernels
+    extras = None
+    if not args.no_diag:
+        extras = {}
+        try:
+            ns64 = min(16, ns)
+            x64 = torch.randn((ns64, n1, n2), dtype=torch.complex64, device=dev) * mask_dev[None]
+            o64 = torch.empty_like(x64)
+            p64 = p3d.PocsPlan(n1, n2, device=local, precision=64)
+            par64 = p3d.make_params(niter=10, thresh_op=c["thresh_op"], thresh_model="exponential", eps=0.0, alpha=c["alpha"])
+            p64.run_device(x64.data_ptr(), mask_dev.data_ptr(), o64.data_ptr(), ns64, par64)
+            p64.event_record(0)
+            p64.run_device(x64.data_ptr(), mask_dev.data_ptr(), o64.data_ptr(), ns64, par64)
+            p64.event_record(1)
+            extras["float64_state_mode"] = {"value": ns64 * 10 / (p64.event_elapsed_ms(0, 1) * 1e-3), "unit": "slice-iterations/s",
+                                            "sample": f"{ns64} slices x 10 iterations, precision=64"}
+            p64.close(); del x64, o64
+        except Exception as ex:          # noqa: BLE001
+            extras["float64_state_mode"] = {"error": str(ex)[:200]}
+        try:
+            import ctypes as C
+            nt_, ntr_ = c["nt"], min(n1 * n2, 262144)
+            xt = torch.randn((nt_, ntr_), dtype=torch.float32, device=dev)
+            ft = torch.empty((nt_ // 2 + 1, ntr_), dtype=torch.complex64, device=dev)
+            lib = _lib.load()
+            res = {}
+            for name, fn in (("time_fft", lambda: lib.p3d_time_fft(local, C.c_void_p(xt.data_ptr()), 1, C.c_void_p(ft.data_ptr()), 1, nt_, nt_, ntr_, 0.05, 725.0, 1, None)),
+                             ("time_ifft", lambda: lib.p3d_time_ifft(local, C.c_void_p(ft.data_ptr()), 1, C.c_void_p(xt.data_ptr()), 1, nt_, nt_, ntr_, 0.05, 725.0, 1, 0))):
+                _lib.check(fn()); _lib.check(fn())
+                ms = C.c_double(); lib.p3d_time_last_kernel_ms(C.byref(ms))
+                nbytes = xt.numel() * 4 + ft.numel() * 8
+                res[name] = {"kernel_ms": ms.value, "algorithmic_GBps": nbytes / max(ms.value, 1e-9) / 1e6}
+            res["sample"] = f"{nt_} samples x {ntr_} traces, compute_real"
+            extras["time_axis"] = res
+            del xt, ft
+        except Exception as ex:          # noqa: BLE001
+            extras["time_axis"] = {"error": str(ex)[:200]}
+
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -405,7 +443,7 @@ def main():
                        "plan": desc, "timing": "CUDA events on the library stream, max over ranks",
                        "wall_ms_per_step": wall_ms_max / args.steps},
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
-            "diag_cufft_chain": diag, "checksum": checksum}
+            "diag_cufft_chain": diag, "extras": extras, "checksum": checksum}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -155,16 +155,16 @@ template <int N_, int E_, int... Rs> struct LinePlan {
 
 // ---- shared-memory accessors ---------------------------------------------------------------------
 // Two buffers (see p3d_fft_reg.cuh).  Column tile: [addr][c], c fastest; row tile: [row][addr].
-template <int C, int LINE> struct ColAcc {
+template <typename T, int C, int LINE> struct ColAcc {
     static constexpr int STRIDE = C;
-    Cx<float>* base;   // already offset by c
-    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (LINE * C); }
+    Cx<T>* base;   // already offset by c
+    __device__ __forceinline__ Cx<T>* line(int buf) const { return base + buf * (LINE * C); }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
-template <int RB, int LINE> struct RowAcc {
+template <typename T, int RB, int LINE> struct RowAcc {
     static constexpr int STRIDE = 1;
-    Cx<float>* base;   // already offset by the row
-    __device__ __forceinline__ Cx<float>* line(int buf) const { return base + buf * (RB * LINE); }
+    Cx<T>* base;   // already offset by the row
+    __device__ __forceinline__ Cx<T>* line(int buf) const { return base + buf * (RB * LINE); }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 }  // namespace p3d

@@ -20,9 +20,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 constexpr int P3D_PREFETCH_DISTANCE = 296;
 
 // ---- column kernel ---------------------------------------------------------------------------------
-template <typename LP, int C, int MINB, bool PF>
+template <typename F, typename LP, int C, int MINB, bool PF>
 __global__ void __launch_bounds__(LP::T* C, MINB)
-k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A, const int op) {
+k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A, const int op) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     const int s = blockIdx.y;
@@ -30,13 +30,13 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     const int c = tid % C, j = tid / C;
     const int col = blockIdx.x * C + c;
     const bool ok = col < G.n2;
-    Cx<float>* __restrict__ Ws = A.W + (long long)s * N * G.n2 + col;
-    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    Cx<F>* __restrict__ Ws = A.W + (long long)s * N * G.n2 + col;
+    ColAcc<F, C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<F>*>(smem_raw) + c;
 
-    Cx<float> v[E];
+    Cx<F> v[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(j + e * T) * G.n2] : cmake<float>(0.f, 0.f);
-    const Cx<float> tau = A.tau[(long long)s * A.niter + A.k];
+    for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(j + e * T) * G.n2] : cmake<F>(F(0), F(0));
+    const Cx<F> tau = A.tau[(long long)s * A.niter + A.k];
     // the (rare) early-exit test comes AFTER the loads were issued, so that its own dependent
     // loads (stop flag, two sums) do not delay them
     if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) return;
@@ -45,31 +45,31 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
         const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + P3D_PREFETCH_DISTANCE;
         const long long by = lin / gridDim.x, bx = lin - by * gridDim.x;
         if (by < gridDim.y && bx * C + c < G.n2) {
-            const Cx<float>* nx = A.W + by * (long long)N * G.n2 + bx * C + c;
+            const Cx<F>* nx = A.W + by * (long long)N * G.n2 + bx * C + c;
 #pragma unroll
             for (int e = 0; e < E; ++e) prefetch_l2(nx + (long long)(j + e * T) * G.n2);
         }
     }
 
-    LP::template fft<-1, 0, float>(v, acc, j, tw);
+    LP::template fft<-1, 0, F>(v, acc, j, tw);
 
-    const float a = tau.x, b = tau.y;
-    const float t2re = a * a - b * b, t2im = 2.f * a * b;
+    const F a = tau.x, b = tau.y;
+    const F t2re = a * a - b * b, t2im = F(2) * a * b;
     if (op == P3D_OP_HARD && !A.exact_tie) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float, false>(v[e], a, b, t2re, t2im);
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, F, false>(v[e], a, b, t2re, t2im);
     } else if (op == P3D_OP_HARD) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float>(v[e], a, b, t2re, t2im);
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, F>(v[e], a, b, t2re, t2im);
     } else if (op == P3D_OP_SOFT) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_SOFT, float>(v[e], a, b, t2re, t2im);
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_SOFT, F>(v[e], a, b, t2re, t2im);
     } else {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_GARROTE, float>(v[e], a, b, t2re, t2im);
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_GARROTE, F>(v[e], a, b, t2re, t2im);
     }
 
-    LP::template fft<+1, (LP::NEXCH & 1), float>(v, acc, j, tw);
+    LP::template fft<+1, (LP::NEXCH & 1), F>(v, acc, j, tw);
 
     if (ok) {
 #pragma unroll
@@ -78,9 +78,9 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
 }
 
 // ---- row kernel ----------------------------------------------------------------------------------
-template <typename LP, int RB, int MINB, bool PF>
+template <typename F, typename LP, int RB, int MINB, bool PF>
 __global__ void __launch_bounds__(LP::T* RB, MINB)
-k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A) {
+k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_s[32];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
@@ -92,14 +92,14 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     const int row = blockIdx.x * RB + rr;
     const bool ok = row < G.n1;
     const long long off = (long long)s * G.n1 * N + (long long)row * N + j;
-    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
-    Cx<float>* __restrict__ Wp = A.W + off;
-    const Cx<float>* __restrict__ Dp = A.D + off;
-    Cx<float>* __restrict__ Op = A.OUT + off;
+    RowAcc<F, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<F>*>(smem_raw) + rr * LP::LINE;
+    Cx<F>* __restrict__ Wp = A.W + off;
+    const Cx<F>* __restrict__ Dp = A.D + off;
+    Cx<F>* __restrict__ Op = A.OUT + off;
 
-    Cx<float> v[E];
+    Cx<F> v[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = ok ? Wp[e * T] : cmake<float>(0.f, 0.f);
+    for (int e = 0; e < E; ++e) v[e] = ok ? Wp[e * T] : cmake<F>(F(0), F(0));
     if (PF && ok && (j & 3) == 0) {
         // the observed data of this tile are needed after the inverse transform: start fetching now;
         // and warm L2 with the W rows of the CTA that will run P3D_PREFETCH_DISTANCE blocks later
@@ -108,7 +108,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
         const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + P3D_PREFETCH_DISTANCE;
         const long long by = lin / gridDim.x, bx = lin - by * gridDim.x;
         if (by < gridDim.y && bx * RB + rr < G.n1) {
-            const Cx<float>* nx = A.W + by * (long long)G.n1 * N + (bx * RB + rr) * (long long)N + j;
+            const Cx<F>* nx = A.W + by * (long long)G.n1 * N + (bx * RB + rr) * (long long)N + j;
 #pragma unroll
             for (int e = 0; e < E; ++e) prefetch_l2(nx + e * T);
         }
@@ -118,25 +118,25 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
     if (stopped != 0) return;
 
-    LP::template fft<+1, 0, float>(v, acc, j, tw);
+    LP::template fft<+1, 0, F>(v, acc, j, tw);
 
-    float part = 0.f;
+    F part = F(0);
     if (ok) {
         // all observed-data loads are issued before the first use (one exposed latency, not E)
-        Cx<float> d[E];
+        Cx<F> d[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) d[e] = Dp[e * T];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const float m = ((mbits >> e) & 1u) ? 1.f : 0.f;
-            const float coef = (1.f - A.alpha * m) * A.inv_n;
-            Cx<float> x = cmake<float>(fmaf(coef, v[e].x, A.alpha * d[e].x), fmaf(coef, v[e].y, A.alpha * d[e].y));
-            part += sqrtf(x.x * x.x + x.y * x.y);
+            const F m = ((mbits >> e) & 1u) ? F(1) : F(0);
+            const F coef = (F(1) - A.alpha * m) * A.inv_n;
+            Cx<F> x = cmake<F>(fma(coef, v[e].x, A.alpha * d[e].x), fma(coef, v[e].y, A.alpha * d[e].y));
+            part += sqrt(x.x * x.x + x.y * x.y);
             if (A.write_out) Op[e * T] = x;
             if (A.adaptive) {
-                const float keep = 1.f - A.alpha * m, om = 1.f - A.alpha;
-                const Cx<float> xt = cmake<float>(A.alpha * d[e].x + keep * x.x, A.alpha * d[e].y + keep * x.y);
-                x = cmake<float>(xt.x + om * (d[e].x - m * x.x), xt.y + om * (d[e].y - m * x.y));
+                const F keep = F(1) - A.alpha * m, om = F(1) - A.alpha;
+                const Cx<F> xt = cmake<F>(A.alpha * d[e].x + keep * x.x, A.alpha * d[e].y + keep * x.y);
+                x = cmake<F>(xt.x + om * (d[e].x - m * x.x), xt.y + om * (d[e].y - m * x.y));
             }
             v[e] = x;
         }
@@ -152,7 +152,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw
     }
     if (A.last) return;
 
-    LP::template fft<-1, (LP::NEXCH & 1), float>(v, acc, j, tw);
+    LP::template fft<-1, (LP::NEXCH & 1), F>(v, acc, j, tw);
 
     if (ok) {
 #pragma unroll
@@ -175,7 +175,7 @@ k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict
     const int row = blockIdx.x * RB + rr;
     const bool ok = row < G.n1;
     const long long off = (long long)s * G.n1 * N + (long long)row * N + j;
-    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    RowAcc<float, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
     const Cx<float>* __restrict__ Dp = A.D + off;
     Cx<float>* __restrict__ Wp = A.W + off;
     Cx<float> v[E];
@@ -236,7 +236,7 @@ k_cols_stats_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restric
     const int col = blockIdx.x * C + c;
     const bool ok = col < G.n2;
     const Cx<float>* __restrict__ Ws = A.W + (long long)s * N * G.n2 + col;
-    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    ColAcc<float, C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
     Cx<float> v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(j + e * T) * G.n2] : cmake<float>(0.f, 0.f);
@@ -279,27 +279,27 @@ __global__ void k_pack_mask(const uint8_t* __restrict__ mask, uint32_t* __restri
 }
 
 // ---- registry ----------------------------------------------------------------------------------------
-template <typename LP, int C, int MINB, bool PF = false>
-static void launch_cols(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
-    constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<float>);
+template <typename LP, int C, int MINB, bool PF = false, typename F = float>
+static void launch_cols(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A, int ns, int op, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<F>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_cols_spec<LP, C, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cols_spec<F, LP, C, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n2 + C - 1) / C, ns);
-    k_cols_spec<LP, C, MINB, PF><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
+    k_cols_spec<F, LP, C, MINB, PF><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
 }
-template <typename LP, int RB, int MINB, bool PF = false>
-static void launch_rows(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {
-    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
+template <typename LP, int RB, int MINB, bool PF = false, typename F = float>
+static void launch_rows(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A, int ns, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<F>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_rows_spec<LP, RB, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_rows_spec<F, LP, RB, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n1 + RB - 1) / RB, ns);
-    k_rows_spec<LP, RB, MINB, PF><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+    k_rows_spec<F, LP, RB, MINB, PF><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
 }
 template <typename LP, int RB, int MINB>
 static void launch_rows_init(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {

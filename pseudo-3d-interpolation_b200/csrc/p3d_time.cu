@@ -153,7 +153,7 @@ k_time_fwd_spec(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
     const int c = tid % C, j = tid / C;
     const long long tr = (long long)blockIdx.x * 2 * C + 2 * c;          // first trace of this pair
     const bool ok = tr < G.ntr;                                          // ntr is even: the pair is complete
-    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    ColAcc<float, C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
 
     Cx<float> v[E];
 #pragma unroll
@@ -199,7 +199,7 @@ k_time_inv_spec(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
     const int c = tid % C, j = tid / C;
     const long long tr = (long long)blockIdx.x * 2 * C + 2 * c;
     const bool ok = tr < G.ntr;
-    ColAcc<C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    ColAcc<float, C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
     Cx<float>* bufA = acc.line(0);
     Cx<float>* bufB = acc.line(1);
 
@@ -296,7 +296,7 @@ k_time_fwd_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
     const int j = tid % T, rr = tid / T;
     const long long ta = ((long long)blockIdx.x * RB + rr) * 2, tb = ta + 1;
     const bool oka = ta < ntr_chunk, okb = tb < ntr_chunk;
-    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    RowAcc<float, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
     const float* __restrict__ pa = xt + ta * G.nt + j;
     const float* __restrict__ pb = xt + tb * G.nt + j;
     Cx<float> v[E];
@@ -339,7 +339,7 @@ k_time_inv_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
     const int j = tid % T, rr = tid / T;
     const long long ta = ((long long)blockIdx.x * RB + rr) * 2, tb = ta + 1;
     const bool oka = ta < ntr_chunk, okb = tb < ntr_chunk;
-    RowAcc<RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    RowAcc<float, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
     Cx<float>* bufA = acc.line(0);
     Cx<float>* bufB = acc.line(1);
     const Cx<float>* __restrict__ ia = Ft + ta * G.nf;

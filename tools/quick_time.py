@@ -38,6 +38,8 @@ def main():
         plan.set_option("force_generic", 1)
     if len(a) > 7:
         plan.set_option("spec_variant", int(a[7]))
+    if len(a) > 9:
+        plan.set_option("lanes", int(a[9]))
     print(plan.describe())
     dx = _lib.DeviceBuffer(x.nbytes); dx.upload(x)
     dm = _lib.DeviceBuffer(mask.nbytes); dm.upload(mask)
