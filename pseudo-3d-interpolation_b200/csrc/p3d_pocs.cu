@@ -50,6 +50,7 @@ struct p3d_plan {
     size_t col_smem = 0, row_smem = 0;
     SpecKernels spec{};              // specialised register-resident kernels when available
     bool force_generic = false;
+    int spec_variant64 = 0;
     int precision = 32;              // 32: fp32 fast path, 64: float64 state mode (p3d_pocs_f64.cu)
     F64Runner* f64 = nullptr;
     int64_t max_slices = 0;
@@ -500,7 +501,8 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     DeviceGuard guard(P->device);
 
     if (P->precision == 64) {
-        if (!P->f64) P->f64 = f64_create(P->device, P->n1, P->n2, &P->ax1, &P->ax2, P->smem_optin);
+        if (!P->f64) { P->f64 = f64_create(P->device, P->n1, P->n2, &P->ax1, &P->ax2, P->smem_optin); f64_install_spec(P->f64, P->spec_variant64); }
+        f64_set_force_generic(P->f64, P->force_generic ? 1 : 0);
         if (P->lanes.empty()) P->lanes.resize(1);
         if (!P->lanes[0].stream) P3D_CUDA(cudaStreamCreateWithFlags(&P->lanes[0].stream, cudaStreamNonBlocking));
         const uint8_t* dmask = nullptr;
@@ -703,6 +705,11 @@ int p3d_plan_describe(p3d_plan* P, char* buf, int64_t buflen) {
     s += std::string("; cols_iter=") + ((P->spec.cols_iter && !P->force_generic) ? P->spec.cols_name : "generic");
     s += std::string("; rows_iter=") + ((P->spec.rows_iter && !P->force_generic) ? P->spec.rows_name : "generic");
     s += "; precision=" + std::to_string(P->precision);
+    if (P->precision == 64) {
+        const SpecKernels64 k64 = select_spec_kernels64(P->n1, P->n2, P->spec_variant64);
+        s += std::string("; cols_iter64=") + ((k64.cols_iter && !P->force_generic) ? k64.cols_name : "generic64");
+        s += std::string("; rows_iter64=") + ((k64.rows_iter && !P->force_generic) ? k64.rows_name : "generic64");
+    }
     s += "; band_slices=" + std::to_string(P->band_slices) + "; sms=" + std::to_string(P->sm_count);
     snprintf(buf, (size_t)buflen, "%s", s.c_str());
     return P3D_OK;
@@ -719,6 +726,10 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     }
     else if (!strcmp(key, "spec_variant")) {
         try { DeviceGuard g(P->device); install_spec(P, (int)value); } catch (const P3dFail& f) { return f.code; }
+    }
+    else if (!strcmp(key, "spec_variant64")) {
+        P->spec_variant64 = (int)value;
+        if (P->f64) { try { DeviceGuard g(P->device); f64_install_spec(P->f64, (int)value); } catch (const P3dFail& f) { return f.code; } }
     }
     else if (!strcmp(key, "max_slices")) { P->max_slices = value; for (auto& L : P->lanes) { cudaStream_t st = L.stream; L.stream = nullptr; free_lane(L); L.stream = st; } }
     else { set_error("unknown option %s", key); return P3D_ERR_BAD_ARG; }

@@ -5,6 +5,7 @@
 // chunked by device memory; built for exactness, not for speed.
 #include "p3d_pocs_f64.h"
 #include "p3d_pocs_launch.h"
+#include "p3d_pocs_spec.cuh"
 #include "p3d_schedule.h"
 
 #include <algorithm>
@@ -22,6 +23,10 @@ struct F64Runner {
     Cx<double>* W = nullptr; Cx<double>* D = nullptr; Cx<double>* OUT = nullptr; Cx<double>* tau = nullptr;
     Cx<float>* io32 = nullptr;           // complex64 staging for host input / output
     double* S = nullptr; int* stop = nullptr; SliceStats* stats = nullptr;
+    SpecKernels64 spec;                  // register-resident iteration kernels (1000 / 2000 / 256 / 200), else generic
+    Cx<double>* tw_cols = nullptr; Cx<double>* tw_rows = nullptr;
+    uint32_t* mbits = nullptr; int64_t mbits_words = 0;
+    int force_generic = 0;
     std::vector<Cx<double>> h_tau; std::vector<double> h_S; std::vector<int> h_stop; std::vector<SliceStats> h_stats;
 };
 
@@ -31,6 +36,23 @@ static void f64_free_buffers(F64Runner* R) {
     R->W = R->D = R->OUT = R->tau = nullptr; R->io32 = nullptr; R->S = nullptr; R->stop = nullptr; R->stats = nullptr;
     R->cap = 0; R->niter_cap = 0;
 }
+
+void f64_install_spec(F64Runner* R, int variant) {
+    R->spec = select_spec_kernels64(R->n1, R->n2, variant);
+    auto upload = [](const std::vector<int>& radices, Cx<double>** dst) {
+        if (*dst) { cudaFree(*dst); *dst = nullptr; }
+        if (radices.empty()) return;
+        std::vector<Cx<double>> t = spec_twiddle_table64(radices);
+        P3D_CUDA(cudaMalloc(dst, sizeof(Cx<double>) * t.size()));
+        P3D_CUDA(cudaMemcpy(*dst, t.data(), sizeof(Cx<double>) * t.size(), cudaMemcpyHostToDevice));
+    };
+    upload(R->spec.cols_radices, &R->tw_cols);
+    upload(R->spec.rows_radices, &R->tw_rows);
+    R->mbits_words = 0;
+}
+void f64_set_force_generic(F64Runner* R, int on) { R->force_generic = on; }
+const char* f64_cols_name(const F64Runner* R) { return (R->spec.cols_iter && !R->force_generic) ? R->spec.cols_name : "generic64"; }
+const char* f64_rows_name(const F64Runner* R) { return (R->spec.rows_iter && !R->force_generic) ? R->spec.rows_name : "generic64"; }
 
 F64Runner* f64_create(int device, int n1, int n2, AxisPlan* ax1, AxisPlan* ax2, size_t smem_optin) {
     F64Runner* R = new F64Runner();
@@ -57,6 +79,7 @@ F64Runner* f64_create(int device, int n1, int n2, AxisPlan* ax1, AxisPlan* ax2, 
         R->cfg.col_threads = pick((long)L1 * C); R->cfg.row_threads = pick((long)L2 * RB);
         { cudaError_t e = generic64_configure(R->cfg); P3D_CUDA(e); }
         P3D_CUDA(cudaStreamCreateWithFlags(&R->st, cudaStreamNonBlocking));
+        f64_install_spec(R, 0);
     } catch (...) { f64_destroy(R); throw; }
     return R;
 }
@@ -64,6 +87,9 @@ F64Runner* f64_create(int device, int n1, int n2, AxisPlan* ax1, AxisPlan* ax2, 
 void f64_destroy(F64Runner* R) {
     if (!R) return;
     f64_free_buffers(R);
+    if (R->tw_cols) cudaFree(R->tw_cols);
+    if (R->tw_rows) cudaFree(R->tw_rows);
+    if (R->mbits) cudaFree(R->mbits);
     if (R->st) cudaStreamDestroy(R->st);
     delete R;
 }
@@ -106,6 +132,20 @@ int f64_run(F64Runner* R, const p3d_pocs_params* prp, const Cx<float>* x, int x_
     const bool adaptive = pr.version == P3D_VERSION_ADAPTIVE;
     const AxisDev<double> a1 = R->ax1->dev64(), a2 = R->ax2->dev64();
     R->cfg.geom.slices_per_mask = (int)std::min<int64_t>(spm, 0x7fffffff);
+    const bool spec_cols = R->spec.cols_iter && !R->force_generic, spec_rows = R->spec.rows_iter && !R->force_generic;
+    if (spec_rows && !schedule_only) {
+        // packed mask words of the register-resident row kernel (rebuilt every run: the mask may have changed)
+        const int64_t n_masks = (n_slices + spm - 1) / spm;
+        const int64_t words = n_masks * (int64_t)R->n1 * R->spec.rows_T;
+        if (words > R->mbits_words || !R->mbits) {
+            if (R->mbits) cudaFree(R->mbits);
+            R->mbits = nullptr; R->mbits_words = 0;
+            P3D_CUDA(cudaMalloc(&R->mbits, sizeof(uint32_t) * words));
+            R->mbits_words = words;
+        }
+        R->spec.pack_mask(dmask, R->mbits, (int)n_masks, R->n1, st);
+        P3D_CUDA(cudaGetLastError());
+    }
 
     for (int64_t first = 0; first < n_slices; first += R->cap) {
         const int64_t count = std::min<int64_t>(R->cap, n_slices - first);
@@ -128,7 +168,7 @@ int f64_run(F64Runner* R, const p3d_pocs_params* prp, const Cx<float>* x, int x_
 
         BandArgs<double> A;
         memset(&A, 0, sizeof(A));
-        A.mask = dmask; A.mbits = nullptr; A.niter = niter; A.eps = pr.eps; A.alpha = pr.alpha;
+        A.mask = dmask; A.mbits = spec_rows ? R->mbits : nullptr; A.exact_tie = 1; A.niter = niter; A.eps = pr.eps; A.alpha = pr.alpha;
         A.inv_n = 1.0 / ((double)R->n1 * (double)R->n2);
         A.W = R->W; A.D = R->D; A.OUT = R->OUT; A.first_slice = first; A.tau = R->tau; A.S = R->S; A.stop = R->stop; A.stats = R->stats;
         const int64_t band_max = 32768;
@@ -202,8 +242,10 @@ int f64_run(F64Runner* R, const p3d_pocs_params* prp, const Cx<float>* x, int x_
             for (int k = 0; k < niter; ++k) {
                 B.k = k; B.last = (k == niter - 1) ? 1 : 0;
                 B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
-                generic64_cols_iter(R->cfg, a1, B, nb, pr.thresh_op, st);
-                generic64_rows_iter(R->cfg, a2, B, nb, st);
+                if (spec_cols) R->spec.cols_iter(R->cfg.geom, R->tw_cols, B, nb, pr.thresh_op, st);
+                else generic64_cols_iter(R->cfg, a1, B, nb, pr.thresh_op, st);
+                if (spec_rows) R->spec.rows_iter(R->cfg.geom, R->tw_rows, B, nb, st);
+                else generic64_rows_iter(R->cfg, a2, B, nb, st);
             }
         }
         P3D_CUDA(cudaGetLastError());

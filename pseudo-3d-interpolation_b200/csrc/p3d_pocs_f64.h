@@ -7,6 +7,10 @@ namespace p3d {
 struct F64Runner;
 F64Runner* f64_create(int device, int n1, int n2, AxisPlan* ax1, AxisPlan* ax2, size_t smem_optin);
 void f64_destroy(F64Runner* R);
+void f64_install_spec(F64Runner* R, int variant);
+void f64_set_force_generic(F64Runner* R, int on);
+const char* f64_cols_name(const F64Runner* R);
+const char* f64_rows_name(const F64Runner* R);
 // x / out: complex64 in host or device memory (x_mem / out_mem); dmask: DEVICE pointer
 int f64_run(F64Runner* R, const p3d_pocs_params* pr, const Cx<float>* x, int x_mem, const uint8_t* dmask, int64_t spm,
             Cx<float>* out, int out_mem, int64_t n_slices, int32_t* niter_out, double* cost_out, double* costs_out,

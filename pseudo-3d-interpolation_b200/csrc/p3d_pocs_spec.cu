@@ -336,8 +336,8 @@ template <typename LP> static std::vector<int> radices_of() {
     return r;
 }
 
-std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices) {
-    std::vector<Cx<float>> t;
+template <typename F> static std::vector<Cx<F>> spec_twiddle_table_t(const std::vector<int>& radices) {
+    std::vector<Cx<F>> t;
     long Ns = 1;
     for (size_t p = 0; p < radices.size(); ++p) {
         const int R = radices[p];
@@ -345,14 +345,16 @@ std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices) {
             for (long k = 0; k < Ns; ++k)
                 for (int r = 0; r < R; ++r) {
                     const double ang = -2.0 * M_PI * (double)((r * k) % (Ns * R)) / (double)(Ns * R);
-                    t.push_back(cmake<float>((float)cos(ang), (float)sin(ang)));
+                    t.push_back(cmake<F>((F)cos(ang), (F)sin(ang)));
                 }
         }
         Ns *= R;
     }
-    if (t.empty()) t.push_back(cmake<float>(1.f, 0.f));
+    if (t.empty()) t.push_back(cmake<F>(F(1), F(0)));
     return t;
 }
+std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices) { return spec_twiddle_table_t<float>(radices); }
+std::vector<Cx<double>> spec_twiddle_table64(const std::vector<int>& radices) { return spec_twiddle_table_t<double>(radices); }
 
 typedef LinePlan<1000, 10, 10, 10, 10> LP1000;
 typedef LinePlan<1000, 20, 10, 10, 10> LP1000E20;
@@ -416,6 +418,48 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else if (variant == 2) P3D_ROWS(LP200, 6, 8, "spec<200,E20,10x20,RB6>");
             else P3D_ROWS(LP200, 3, 12, "spec<200,E20,10x20,RB3>");
             break;
+        default: break;
+    }
+    return k;
+}
+
+// ---- float64 state mode: the same iteration kernels instantiated for complex128 -----------------------
+// (16-byte elements: E = 10 / 8 keeps the line in <= 64 data registers)
+typedef LinePlan<256, 8, 8, 8, 4> LP256E8;
+typedef LinePlan<200, 10, 10, 10, 2> LP200E10;
+
+#define P3D_COLS64(LP, C, MINB, NAME) do { k.cols_iter = launch_cols<LP, C, MINB, false, double>; \
+                                           k.cols_name = NAME; k.cols_radices = radices_of<LP>(); } while (0)
+#define P3D_ROWS64(LP, RB, MINB, NAME) do { k.rows_iter = launch_rows<LP, RB, MINB, false, double>; \
+                                            k.rows_name = NAME; k.rows_radices = radices_of<LP>(); \
+                                            k.pack_mask = launch_pack<LP>; k.rows_T = LP::T; } while (0)
+
+SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant) {
+    SpecKernels64 k;
+    switch (n_iline) {
+        case 1000:
+            if (variant == 1) P3D_COLS64(LP1000, 4, 1, "spec64<1000,E10,10x10x10,C4,1cta>");
+            else if (variant == 2) P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta>");
+            else              P3D_COLS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,C2,2cta>");
+            break;
+        case 2000:
+            if (variant == 1) P3D_COLS64(LP2000, 1, 3, "spec64<2000,E10,10x10x10x2,C1,3cta>");
+            else              P3D_COLS64(LP2000, 2, 1, "spec64<2000,E10,10x10x10x2,C2,1cta>");
+            break;
+        case 256:  P3D_COLS64(LP256E8, 8, 3, "spec64<256,E8,8x8x4,C8>"); break;
+        case 200:  P3D_COLS64(LP200E10, 8, 4, "spec64<200,E10,10x10x2,C8>"); break;
+        default: break;
+    }
+    switch (n_xline) {
+        case 1000:
+            if (variant == 1) P3D_ROWS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,RB2,2cta>");
+            else              P3D_ROWS64(LP1000, 1, 5, "spec64<1000,E10,10x10x10,RB1,5cta>");
+            break;
+        case 2000:
+            P3D_ROWS64(LP2000, 1, 2, "spec64<2000,E10,10x10x10x2,RB1,2cta>");
+            break;
+        case 256:  P3D_ROWS64(LP256E8, 4, 5, "spec64<256,E8,8x8x4,RB4>"); break;
+        case 200:  P3D_ROWS64(LP200E10, 4, 6, "spec64<200,E10,10x10x2,RB4>"); break;
         default: break;
     }
     return k;

@@ -28,4 +28,20 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant = 0);
 // Host: concatenated [k][R] tables of every twiddled pass (see p3d_fft_reg.cuh), computed in double.
 std::vector<Cx<float>> spec_twiddle_table(const std::vector<int>& radices);
 
+
+// ---- float64 state mode ("precision" = 64): iteration kernels only (the once-per-slice kernels stay generic)
+typedef void (*ColsIterLaunch64)(const PocsGeom&, const Cx<double>* tw, const BandArgs<double>&, int nslices, int op, cudaStream_t);
+typedef void (*RowsIterLaunch64)(const PocsGeom&, const Cx<double>* tw, const BandArgs<double>&, int nslices, cudaStream_t);
+struct SpecKernels64 {
+    ColsIterLaunch64 cols_iter = nullptr;
+    RowsIterLaunch64 rows_iter = nullptr;
+    PackMaskLaunch pack_mask = nullptr;
+    const char* cols_name = "generic64";
+    const char* rows_name = "generic64";
+    std::vector<int> cols_radices, rows_radices;
+    int rows_T = 0;
+};
+SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant = 0);
+std::vector<Cx<double>> spec_twiddle_table64(const std::vector<int>& radices);
+
 }  // namespace p3d

@@ -297,6 +297,32 @@ def test_f64_mode_ill_conditioned_spec_shape(p3d):
     assert rel_l2(y[0], ref) <= 2e-7, rel_l2(y[0], ref)
 
 
+@pytest.mark.parametrize("shape", [(200, 200), (256, 256), (200, 256), (1000, 48), (48, 2000)])
+@pytest.mark.parametrize("op,model,alpha,version", [("hard", "exponential", 1.0, "regular"), ("soft", "linear", 0.7, "regular"),
+                                                     ("garrote", "data-driven", 1.0, "adaptive")])
+def test_f64_mode_register_kernels_match_generic(shape, op, model, alpha, version, p3d):
+    """float64 state mode: the register-resident complex128 iteration kernels (1000 / 2000 / 256 / 200, also
+    mixed with a generic axis) against the generic complex128 kernels and the float64 oracle."""
+    x, mask = make_input(dict(seed=5, shape=shape, keep=0.3, nwaves=4))
+    x = np.stack([x, 0.5 * x[::-1, ::-1] * mask]).astype(np.complex64)
+    params = dict(niter=9, thresh_op=op, thresh_model=model, eps=0.0, alpha=alpha, p_max=0.99, p_min=1e-3)
+    plan = p3d.PocsPlan(*shape, precision=64)
+    assert "spec64<" in plan.describe()
+    y, info = plan.run(x, mask, version=version, want_costs=True, **params)
+    gen = p3d.PocsPlan(*shape, precision=64)
+    gen.set_option("force_generic", 1)
+    assert "spec64<" not in gen.describe()
+    yg, infog = gen.run(x, mask, version=version, want_costs=True, **params)
+    assert rel_l2(y, yg) <= 2e-7
+    np.testing.assert_allclose(info["costs"], infog["costs"], rtol=1e-3, atol=1e-22)   # tiny costs = cancelling sums
+    for i in range(2):
+        ref = orc.pocs_slice(x[i].astype(np.complex128), mask, version=version, **params)
+        assert rel_l2(y[i], ref) <= 2e-7, rel_l2(y[i], ref)
+    if alpha == 1.0 and version == "regular":
+        obs = mask == 1
+        assert np.array_equal(y[:, obs], x[:, obs])
+
+
 def test_f64_mode_data_driven_and_schedule(p3d):
     case = CASES[4]
     x, mask = make_input(case)

@@ -1,6 +1,6 @@
 """Quick device-resident timing of the POCS iteration kernels (development helper).
 
-    python tools/quick_time.py [n_il] [n_xl] [n_slices] [niter] [band_slices] [op] [force_generic]
+    python tools/quick_time.py [n_il] [n_xl] [n_slices] [niter] [band_slices] [op] [force_generic] [spec_variant] [precision] [lanes] [spec_variant64]
 """
 import os
 import sys
@@ -40,6 +40,8 @@ def main():
         plan.set_option("spec_variant", int(a[7]))
     if len(a) > 9:
         plan.set_option("lanes", int(a[9]))
+    if len(a) > 10:
+        plan.set_option("spec_variant64", int(a[10]))
     print(plan.describe())
     dx = _lib.DeviceBuffer(x.nbytes); dx.upload(x)
     dm = _lib.DeviceBuffer(mask.nbytes); dm.upload(mask)
