@@ -101,6 +101,14 @@ int p3d_pocs_schedule(p3d_plan* plan, const p3d_pocs_params* params, const void*
 int p3d_fft2(p3d_plan* plan, const void* x, int x_mem, void* out, int out_mem, int64_t n_slices,
              int inverse);
 
+/* kx-ky domain filter of a stack of slices: out = ifft2(filt * fft2(x)) per slice, the arithmetic of
+ * remove_acquisition_footprint (cube_postprocessing_3D.py:254) and spatial_antialiasing (:342); the
+ * caller takes the real part.  Runs the three fused passes of one POCS iteration (fp32).
+ *   x, out : (n_slices, n_iline, n_xline) complex64, host or device
+ *   filt   : (n_iline, n_xline) float32 in FFT order (the reference's np.fft.ifftshift(ffilter)) */
+int p3d_kxky_filter_run(p3d_plan* plan, const void* x, int x_mem, const float* filt, int filt_mem,
+                        void* out, int out_mem, int64_t n_slices);
+
 /* Time-axis forward transform of step 12 (cube_apply_FFT.py:240-254):
  *   x   : (nt, n_traces) float32, time-major            (n_traces = n_iline * n_xline)
  *   out : (nf, n_traces) complex64, nf = nfft/2+1 (compute_real) or nfft, fftfreq/rfftfreq order

@@ -47,6 +47,7 @@ SIGNATURES = {
     "p3d_pocs_run": (C.c_int, [C.c_void_p, C.POINTER(PocsParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "p3d_pocs_schedule": (C.c_int, [C.c_void_p, C.POINTER(PocsParams), C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "p3d_kxky_filter_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64]),
     "p3d_fft2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "p3d_time_fft": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                C.c_double, C.c_double, C.c_int, C.c_void_p]),

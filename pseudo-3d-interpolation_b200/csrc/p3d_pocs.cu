@@ -58,6 +58,8 @@ struct p3d_plan {
     int n_lanes = 0;                 // 0 = auto
     std::vector<Lane> lanes;
     uint8_t* d_mask = nullptr; int64_t d_mask_bytes = 0;
+    uint8_t* d_zero_mask = nullptr;                             // kx-ky filter mode: all-zero mask plane
+    float* d_filt = nullptr;                                    // kx-ky filter mode: staged filter plane
     uint32_t* d_mbits = nullptr; int64_t d_mbits_words = 0;    // packed mask of the specialised row kernel
     Cx<float>* spec_tw_cols = nullptr;                          // per-pass twiddle tables (p3d_fft_reg.cuh)
     Cx<float>* spec_tw_rows = nullptr;
@@ -302,6 +304,7 @@ struct RunCtx {
     int32_t* niter_out; double* cost_out; double* costs_out;
     double* tau_out;            // schedule-only mode
     bool schedule_only;
+    const float* filt;          // kx-ky filter mode (device pointer) or null
 };
 
 // collect results of the chunk pending on a lane
@@ -361,6 +364,31 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     memset(&A, 0, sizeof(A));
     A.mask = R.dmask; A.mbits = R.dmbits; A.niter = niter; A.eps = pr.eps; A.alpha = (float)pr.alpha;
     A.inv_n = (float)(1.0 / ((double)P->n1 * (double)P->n2));
+    A.filt = R.filt;
+
+    if (R.filt) {
+        // kx-ky filter mode: out = ifft2(filt * fft2(x)) with the three fused passes of one POCS iteration
+        // (row FFT | column FFT * filt, column IFFT | row IFFT / (N1 N2)); alpha = 0 and an all-zero mask
+        // turn the re-insertion into the plain scaling.
+        const int64_t band_max = 32768;
+        for (int64_t b0 = 0; b0 < count; b0 += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, count - b0);
+            BandArgs<float> B = A;
+            B.W = L.W + b0 * ne; B.D = D + b0 * ne; B.OUT = OUT + b0 * ne; B.first_slice = 0;
+            B.tau = L.tau + b0 * niter; B.S = L.S + b0 * (niter + 1); B.stop = L.stop + b0; B.stats = L.stats + b0;
+            B.adaptive = 0; B.accum = 0; B.store_x0 = 0;
+            launch_rows_init(P, st, B, nb);
+            B.k = 0; B.last = 1; B.write_out = 1;
+            launch_cols_iter(P, st, B, nb, P3D_OP_FILTER);
+            launch_rows_iter(P, st, B, nb);
+        }
+        if (R.out_mem == P3D_MEM_HOST)
+            P3D_CUDA(cudaMemcpyAsync(R.out + first * ne, OUT, sizeof(Cx<float>) * ne * count, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(L.h_S, L.S, sizeof(double) * count * (niter + 1), cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(L.h_stop, L.stop, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+        L.pending = true; L.p_first = first; L.p_count = count;
+        return;
+    }
     const bool data_driven = pr.thresh_model == P3D_MODEL_DATA_DRIVEN;
     const bool adaptive = pr.version == P3D_VERSION_ADAPTIVE;
     A.exact_tie = (pr.thresh_model == P3D_MODEL_INVERSE_PROPORTIONAL || data_driven || pr.decay_factors) ? 1 : 0;
@@ -488,7 +516,7 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
 
 int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, const uint8_t* mask,
              int64_t spm, void* out, int out_mem, int64_t n_slices, int32_t* niter_out, double* cost_out,
-             double* costs_out, double* tau_out, bool schedule_only) {
+             double* costs_out, double* tau_out, bool schedule_only, const float* filt = nullptr) {
     P3D_REQUIRE(P && pr && x, P3D_ERR_BAD_ARG, "null plan / params / x");
     P3D_REQUIRE(n_slices >= 0, P3D_ERR_BAD_ARG, "n_slices must be >= 0");
     P3D_REQUIRE(pr->niter >= 1, P3D_ERR_BAD_ARG, "niter must be >= 1 (got %d)", pr->niter);
@@ -500,7 +528,7 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     if (spm <= 0) spm = n_slices;
     DeviceGuard guard(P->device);
 
-    if (P->precision == 64) {
+    if (P->precision == 64 && !filt) {
         if (!P->f64) { P->f64 = f64_create(P->device, P->n1, P->n2, &P->ax1, &P->ax2, P->smem_optin); f64_install_spec(P->f64, P->spec_variant64); }
         f64_set_force_generic(P->f64, P->force_generic ? 1 : 0);
         if (P->lanes.empty()) P->lanes.resize(1);
@@ -542,7 +570,7 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     R.P = P; R.pr = pr; R.x = (const Cx<float>*)x; R.x_mem = x_mem; R.spm = spm;
     R.out = (Cx<float>*)out; R.out_mem = out_mem; R.niter_out = niter_out; R.cost_out = cost_out;
     R.costs_out = costs_out; R.tau_out = tau_out; R.schedule_only = schedule_only;
-    R.dmask = nullptr; R.dmbits = nullptr;
+    R.dmask = nullptr; R.dmbits = nullptr; R.filt = filt;
     if (!schedule_only) {
         const int64_t n_masks = (n_slices + spm - 1) / spm;
         ensure_mask(P, mask, n_masks * (int64_t)P->n1 * P->n2, x_mem, P->lanes[0].stream, &R.dmask);
@@ -609,6 +637,8 @@ int p3d_plan_destroy(p3d_plan* P) {
     P->ax1.release(); P->ax2.release();
     if (P->d_mask) cudaFree(P->d_mask);
     if (P->d_mbits) cudaFree(P->d_mbits);
+    if (P->d_zero_mask) cudaFree(P->d_zero_mask);
+    if (P->d_filt) cudaFree(P->d_filt);
     if (P->f64) f64_destroy(P->f64);
     if (P->spec_tw_cols) cudaFree(P->spec_tw_cols);
     if (P->spec_tw_rows) cudaFree(P->spec_tw_rows);
@@ -633,6 +663,34 @@ int p3d_pocs_schedule(p3d_plan* plan, const p3d_pocs_params* params, const void*
     P3D_REQUIRE(tau_out, P3D_ERR_BAD_ARG, "tau_out is null");
     return run_impl(plan, params, x, x_mem, nullptr, n_slices, nullptr, P3D_MEM_HOST, n_slices, nullptr, nullptr,
                     nullptr, tau_out, true);
+    P3D_CATCH
+}
+
+int p3d_kxky_filter_run(p3d_plan* P, const void* x, int x_mem, const float* filt, int filt_mem, void* out, int out_mem,
+                        int64_t n_slices) {
+    P3D_TRY
+    P3D_REQUIRE(P && x && filt && out, P3D_ERR_BAD_ARG, "null argument");
+    if (n_slices == 0) return P3D_OK;
+    const int64_t ne = (int64_t)P->n1 * P->n2;
+    const float* dfilt = filt;
+    {
+        DeviceGuard guard(P->device);
+        if (!P->d_zero_mask) { P3D_CUDA(cudaMalloc(&P->d_zero_mask, ne)); P3D_CUDA(cudaMemset(P->d_zero_mask, 0, ne)); }
+        if (filt_mem == P3D_MEM_HOST) {
+            if (!P->d_filt) P3D_CUDA(cudaMalloc(&P->d_filt, sizeof(float) * ne));
+            P3D_CUDA(cudaMemcpy(P->d_filt, filt, sizeof(float) * ne, cudaMemcpyHostToDevice));
+            dfilt = P->d_filt;
+        }
+    }
+    p3d_pocs_params pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.niter = 1; pr.thresh_op = P3D_OP_HARD; pr.thresh_model = P3D_MODEL_EXPONENTIAL; pr.q = 1.0; pr.alpha = 0.0; pr.p_max = 0.99; pr.p_min = 1e-5;
+    // the zero mask lives on the device: tell run_impl so by passing it with a device-resident x, or stage it
+    // through ensure_mask's host path (x_mem host => the mask pointer must be host memory)
+    std::vector<uint8_t> hzero;
+    const uint8_t* mask = P->d_zero_mask;
+    if (x_mem == P3D_MEM_HOST) { hzero.assign((size_t)ne, 0); mask = hzero.data(); }
+    return run_impl(P, &pr, x, x_mem, mask, n_slices, out, out_mem, n_slices, nullptr, nullptr, nullptr, nullptr, false, dfilt);
     P3D_CATCH
 }
 

@@ -56,6 +56,7 @@ cudaError_t generic_configure(const GenericCfg& cfg) {
     P3D_SET((k_cols_generic<float, 1, P3D_OP_HARD>), c.col_smem);
     P3D_SET((k_cols_generic<float, 1, P3D_OP_SOFT>), c.col_smem);
     P3D_SET((k_cols_generic<float, 1, P3D_OP_GARROTE>), c.col_smem);
+    P3D_SET((k_cols_generic<float, 1, P3D_OP_FILTER>), c.col_smem);
     P3D_SET((k_rows_generic<float, 0>), c.row_smem);
     P3D_SET((k_rows_generic<float, 1>), c.row_smem);
     P3D_SET(k_fft2_rows<-1>, c.row_smem); P3D_SET(k_fft2_rows<+1>, c.row_smem);
@@ -77,6 +78,7 @@ void generic_cols_iter(const GenericCfg& c, const AxisDev<float>& ax1, const Ban
     switch (op) {
         case P3D_OP_HARD: k_cols_generic<float, 1, P3D_OP_HARD><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
         case P3D_OP_SOFT: k_cols_generic<float, 1, P3D_OP_SOFT><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
+        case P3D_OP_FILTER: k_cols_generic<float, 1, P3D_OP_FILTER><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
         default:          k_cols_generic<float, 1, P3D_OP_GARROTE><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
     }
 }

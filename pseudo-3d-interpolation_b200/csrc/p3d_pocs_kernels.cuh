@@ -88,7 +88,12 @@ template <typename T> struct BandArgs {
     T alpha, inv_n;
     int write_out, last, adaptive, store_x0, accum;
     int exact_tie;               // thresholds derived from |X0| values (inverse-proportional): honour exact ties
+    const float* filt;           // kx-ky filter mode (P3D_OP_FILTER): real (n1, n2) plane multiplied into the spectrum
 };
+
+// internal "threshold operator": multiply the spectrum by a real filter plane instead of thresholding
+// (cube_postprocessing_3D.py:254,342  ifft2(filter * fft2(slice)))
+#define P3D_OP_FILTER 3
 
 // ---------------------------------------------------------------------------------------------
 // threshold operators with the reference's complex-tau semantics
@@ -255,7 +260,8 @@ __global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_
     for (int w = tid; w < tot; w += nth) {
         const int i = w / nc, c = w - i * nc;
         Cx<T>* p = X + i * G.C + c;
-        *p = apply_threshold<OP, T>(*p, a, b, t2re, t2im);
+        if (OP == P3D_OP_FILTER) { const T h = (T)A.filt[(long long)i * G.n2 + c0 + c]; *p = cmake<T>(p->x * h, p->y * h); }
+        else *p = apply_threshold<OP, T>(*p, a, b, t2re, t2im);
     }
     __syncthreads();
     Cx<T>* Y = line_fft<+1, T>(X, other, tg, ax1, tid, nth);

@@ -64,9 +64,14 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     } else if (op == P3D_OP_SOFT) {
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_SOFT, F>(v[e], a, b, t2re, t2im);
-    } else {
+    } else if (op == P3D_OP_GARROTE) {
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_GARROTE, F>(v[e], a, b, t2re, t2im);
+    } else {
+        // kx-ky filter mode: real filter plane, same (row, column) position as the coefficient
+        const float* __restrict__ H = A.filt + col;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const F h = ok ? (F)__ldg(H + (long long)(j + e * T) * G.n2) : F(0); v[e] = cmake<F>(v[e].x * h, v[e].y * h); }
     }
 
     LP::template fft<+1, (LP::NEXCH & 1), F>(v, acc, j, tw);

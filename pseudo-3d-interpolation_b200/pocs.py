@@ -206,6 +206,28 @@ class PocsPlan:
             _lib.check(_lib.load().p3d_pocs_schedule(self._h, C.byref(params), _lib.ptr(x), _lib.MEM_HOST, x.shape[0], _lib.ptr(tau)))
         return tau[..., 0] + 1j * tau[..., 1]
 
+    def kxky_filter(self, x, filt, out=None):
+        """``ifft2(filt * fft2(x))`` per slice (complex64).  ``filt``: real (n_iline, n_xline) plane in FFT order."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        x3 = x[None] if x.ndim == 2 else x
+        if x3.shape[1:] != (self.n_iline, self.n_xline):
+            raise ValueError(f"slice shape {x3.shape[1:]} does not match the plan ({self.n_iline}, {self.n_xline})")
+        filt = np.ascontiguousarray(filt, dtype=np.float32)
+        if filt.shape != (self.n_iline, self.n_xline):
+            raise ValueError(f"filter shape {filt.shape} does not match the plan")
+        if out is None:
+            out = np.empty_like(x3)
+        with self._lock:
+            _lib.check(_lib.load().p3d_kxky_filter_run(self._h, _lib.ptr(x3), _lib.MEM_HOST, _lib.ptr(filt), _lib.MEM_HOST,
+                                                       _lib.ptr(out), _lib.MEM_HOST, x3.shape[0]))
+        return out[0] if x.ndim == 2 else out
+
+    def kxky_filter_device(self, x_ptr, filt_ptr, out_ptr, n_slices):
+        """Device-resident variant of :meth:`kxky_filter` (raw device pointers)."""
+        with self._lock:
+            _lib.check(_lib.load().p3d_kxky_filter_run(self._h, C.c_void_p(int(x_ptr)), _lib.MEM_DEVICE, C.c_void_p(int(filt_ptr)),
+                                                       _lib.MEM_DEVICE, C.c_void_p(int(out_ptr)), _lib.MEM_DEVICE, int(n_slices)))
+
     def fft2(self, x, inverse=False):
         x = np.ascontiguousarray(x, dtype=np.complex64)
         x3 = x[None] if x.ndim == 2 else x
