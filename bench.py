@@ -227,6 +227,16 @@ def main():
     from pseudo_3d_interpolation_b200 import _lib
 
     _lib.require_gpu()
+    numa = "numa: not bound (P3D_NUMA_BIND=0)"
+    if os.environ.get("P3D_NUMA_BIND", "1") != "0" and world > 1:
+        from pseudo_3d_interpolation_b200.distributed import bind_to_gpu_numa_node
+        gi = local
+        if os.environ.get("CUDA_VISIBLE_DEVICES"):
+            try:
+                gi = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+            except Exception:          # noqa: BLE001
+                gi = local
+        numa = bind_to_gpu_numa_node(gi)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -455,7 +465,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c64 (fp32 complex)", "data": "synthetic",
             "config": {"workload": cfg_workload, "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2" % (ns * n1 * n2 * 8 / 1e9),
-                       "plan": desc, "timing": "CUDA events on the library stream, max over ranks",
+                       "plan": desc, "host": numa + f"; {os.cpu_count()} cpus", "timing": "CUDA events on the library stream, max over ranks",
                        "wall_ms_per_step": wall_ms_max / args.steps},
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
             "diag_cufft_chain": diag, "extras": extras, "checksum": checksum}

@@ -14,6 +14,55 @@ import numpy as np
 from .pocs import band_bounds
 
 
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int, sysfs="/sys"):
+    """NUMA node of a CUDA device from its PCI address (``/sys/bus/pci/devices/<bdf>/numa_node``); None if unknown."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()
+        if len(bdf.split(":")[0]) == 8:           # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        with open(f"{sysfs}/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:            # noqa: BLE001
+        return None
+
+
+def bind_to_gpu_numa_node(device_index: int, sysfs="/sys"):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned staging buffers are
+    allocated, so that they are first-touched on the memory next to the GPU's PCIe root and H2D / D2H copies do
+    not cross the socket interconnect (one process per GPU, as the reference's LocalCluster workers).
+    Returns a short description of what was done; never raises."""
+    import os
+    node = gpu_numa_node(device_index, sysfs)
+    if node is None:
+        return "numa: unknown (not bound)"
+    try:
+        with open(f"{sysfs}/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return f"numa: node {node} has no allowed cpus (not bound)"
+        os.sched_setaffinity(0, allowed)
+        return f"numa: gpu {device_index} -> node {node}, {len(allowed)} cpus"
+    except Exception as ex:      # noqa: BLE001
+        return f"numa: bind failed ({ex})"
+
+
 def rank_band(n_slices: int, rank: int, world: int):
     return band_bounds(n_slices, world)[rank]
 
