@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--slices", type=int, default=0, help="slices per GPU per step (0 = config default)")
     ap.add_argument("--niter", type=int, default=0)
     ap.add_argument("--band", type=int, default=-1, help="band_slices override (-1 = plan default)")
+    ap.add_argument("--lanes", type=int, default=0, help="copy/compute lanes of the host-buffer path (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-diag", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -314,6 +315,9 @@ def main():
         del x_dev, out_dev
         torch.cuda.empty_cache()
 
+        if args.lanes > 0:
+            plan.set_option("lanes", args.lanes)
+
         def step_e2e():
             plan.run(hx.array, hm.array, out=ho.array, params=params)
 
@@ -332,7 +336,7 @@ def main():
         e2e = {"value": total_its_per_step * (ns_e / ns) * args.steps / (float(te[0]) * 1e-3), "unit": "slice-iterations/s",
                "h2d_bytes_per_step": int(hx.nbytes + hm.nbytes), "d2h_bytes_per_step": int(ho.nbytes + ns_e * (niter + 2) * 8),
                "ms_per_step": float(te[0]) / args.steps, "slices_per_gpu_per_step": ns_e,
-               "api": "PocsPlan.run -> p3d_pocs_run(host pinned in/out)"}
+               "api": "PocsPlan.run -> p3d_pocs_run(host pinned in/out)", "lanes": args.lanes if args.lanes > 0 else "auto"}
         checksum = float(np.abs(ho.array[0]).sum())
     else:
         checksum = float(out_dev[0].abs().sum())
