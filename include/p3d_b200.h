@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define P3D_ABI_VERSION 1
+#define P3D_ABI_VERSION 2
 
 typedef enum {
     P3D_OK = 0,
@@ -61,6 +61,11 @@ typedef struct {
     int32_t decay_factors;    /* decay_kind == 'factors': tau_max = p_max, tau_min = p_min       */
     int32_t absmax_threshold; /* 0 = reference-exact complex lexicographic max (default);
                                  1 = real max|X0| ("max-amplitude" of the docs), opt-in extra   */
+    int32_t thresh_percentile;/* '<op>-percentile' operators (functions/POCS.py:43-58): the scheduled value
+                                 tau_k in [0, 100] is a percentile and the threshold of iteration k is
+                                 np.percentile(|X_k|, tau_k) of the slice's current spectrum; requires
+                                 decay_factors != 0 and a linear / exponential schedule (as the reference,
+                                 where anything else fails inside np.percentile)                    */
 } p3d_pocs_params;
 
 typedef struct p3d_plan p3d_plan;

@@ -48,6 +48,9 @@ CASES = [
     dict(name="exponential_q2", seed=22, shape=(45, 35), params=dict(niter=18, thresh_op="garrote", thresh_model="exponential-2", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-4)),
     dict(name="default_eps_hard", seed=23, shape=(64, 50), params=dict(niter=100, thresh_op="hard", thresh_model="exponential", eps=1e-9, alpha=1.0, p_max=0.99, p_min=1e-5)),
     dict(name="all_zero", seed=24, shape=(16, 20), all_zero=True, params=dict(niter=10, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0)),
+    dict(name="soft_percentile_linear", seed=26, shape=(48, 52), params=dict(niter=12, thresh_op="soft-percentile", thresh_model="linear", eps=0.0, alpha=1.0, p_max=99.5, p_min=20.0, decay_kind="factors")),
+    dict(name="garrote_percentile_exp", seed=27, shape=(40, 64), noise=0.01, params=dict(niter=10, thresh_op="garrote-percentile", thresh_model="exponential", eps=0.0, alpha=0.8, p_max=99.0, p_min=5.0, decay_kind="factors")),
+    dict(name="hard_percentile_exp", seed=28, shape=(56, 44), params=dict(niter=10, thresh_op="hard-percentile", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=99.9, p_min=50.0, decay_kind="factors")),
     dict(name="bluestein_sizes", seed=25, shape=(37, 58), params=dict(niter=12, thresh_op="soft", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-3)),
 ]
 

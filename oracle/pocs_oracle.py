@@ -131,6 +131,10 @@ def apply_threshold(X, tau, kind="hard"):
     # array): numpy >= 2 treats numpy scalars as strongly typed, so a complex128 tau promotes a
     # complex64 spectrum to complex128 in the soft / garrote branches exactly as the reference
     # does, and a real tau uses real division (a / r) where a complex tau uses complex division.
+    if kind.endswith("-percentile"):
+        # '<op>-percentile' wrappers (functions/POCS.py:43-58): the scheduled value is a percentile of |X|
+        tau = np.percentile(np.abs(X), tau)
+        kind = kind[: -len("-percentile")]
     a, b = np.real(tau), np.imag(tau)
     r = np.abs(X)
     if kind == "hard":

@@ -27,7 +27,7 @@ class PocsParams(C.Structure):
         ("niter", C.c_int32), ("thresh_op", C.c_int32), ("thresh_model", C.c_int32), ("version", C.c_int32),
         ("q", C.c_double), ("eps", C.c_double), ("alpha", C.c_double), ("p_max", C.c_double), ("p_min", C.c_double),
         ("p_min_adaptive", C.c_int32), ("sqrt_decay", C.c_int32), ("decay_factors", C.c_int32),
-        ("absmax_threshold", C.c_int32),
+        ("absmax_threshold", C.c_int32), ("thresh_percentile", C.c_int32),
     ]
 
 

@@ -64,6 +64,8 @@ struct p3d_plan {
     Cx<float>* spec_tw_cols = nullptr;                          // per-pass twiddle tables (p3d_fft_reg.cuh)
     Cx<float>* spec_tw_rows = nullptr;
     void* cub_temp = nullptr; size_t cub_temp_bytes = 0;
+    // percentile operators: spectrum scratch + |X| keys of a few slices
+    Cx<float>* pct_scr = nullptr; unsigned int* pct_keys = nullptr; unsigned int* pct_sorted = nullptr; int64_t pct_slices = 0;
     cudaEvent_t ev[8] = {nullptr};
     // profiling
     bool profiling = false;
@@ -248,6 +250,28 @@ __global__ void k_pick_tau(const unsigned long long* sorted_desc, const SliceSta
     }
 }
 
+// ---- percentile operators (functions/POCS.py:43-58): tau_k = np.percentile(|X_k|, q_k) per slice and iteration ----
+__global__ void k_abs_keys(const Cx<float>* __restrict__ X, unsigned int* __restrict__ keys, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const Cx<float> v = X[i];
+        keys[i] = __float_as_uint(sqrtf(v.x * v.x + v.y * v.y));      // non-negative floats order like their bit patterns
+    }
+}
+// numpy's default 'linear' percentile: virtual index q/100 * (n-1), _lerp between the two neighbours
+__global__ void k_pick_percentile(const unsigned int* __restrict__ sorted, long long n, Cx<float>* tau_sk) {
+    const double q = (double)tau_sk->x;
+    const double pos = q / 100.0 * (double)(n - 1);
+    long long lo = (long long)floor(pos);
+    lo = lo < 0 ? 0 : (lo > n - 1 ? n - 1 : lo);
+    const long long hi = lo + 1 > n - 1 ? n - 1 : lo + 1;
+    const double t = pos - (double)lo;
+    const double a = (double)__uint_as_float(sorted[lo]), b = (double)__uint_as_float(sorted[hi]);
+    const double diff = b - a;
+    double r = a + diff * t;
+    if (t >= 0.5) r = b - diff * (1.0 - t);
+    *tau_sk = cmake<float>((float)r, 0.f);
+}
+
 // float statistics of a slice -> inputs of the host schedule (p3d_schedule.h)
 ScheduleStats stats_f32(const SliceStats& st) {
     ScheduleStats s;
@@ -295,6 +319,39 @@ int64_t auto_capacity(p3d_plan* P, int64_t n_slices, int nbuf_per_lane, int lane
     cap = std::max<int64_t>(1, std::min<int64_t>(cap, n_slices));
     if (P->max_slices > 0) cap = std::min<int64_t>(cap, P->max_slices);
     return std::min<int64_t>(cap, 60000);
+}
+
+// tau[s][k] holds the scheduled percentile q_k on entry and the threshold np.percentile(|colFFT(W_s)|, q_k) on exit
+void percentile_thresholds(p3d_plan* P, cudaStream_t st, const BandArgs<float>& B, int nb, int k) {
+    const int64_t ne = (int64_t)P->n1 * P->n2;
+    if (!P->pct_scr) {
+        P->pct_slices = std::max<int64_t>(1, std::min<int64_t>(64, (int64_t)(256e6 / (8.0 * (double)ne))));
+        P3D_CUDA(cudaMalloc(&P->pct_scr, sizeof(Cx<float>) * ne * P->pct_slices));
+        P3D_CUDA(cudaMalloc(&P->pct_keys, sizeof(unsigned int) * ne));
+        P3D_CUDA(cudaMalloc(&P->pct_sorted, sizeof(unsigned int) * ne));
+    }
+    size_t need = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, (unsigned int*)nullptr, (unsigned int*)nullptr, (long long)ne, 0, 32, st);
+    if (need > P->cub_temp_bytes) {
+        P3D_CUDA(cudaStreamSynchronize(st));
+        if (P->cub_temp) cudaFree(P->cub_temp);
+        P->cub_temp = nullptr; P->cub_temp_bytes = 0;
+        P3D_CUDA(cudaMalloc(&P->cub_temp, need)); P->cub_temp_bytes = need;
+    }
+    prof_begin(P, st, 6);
+    for (int64_t s0 = 0; s0 < nb; s0 += P->pct_slices) {
+        const int cnt = (int)std::min<int64_t>(P->pct_slices, nb - s0);
+        P3D_CUDA(cudaMemcpyAsync(P->pct_scr, B.W + s0 * ne, sizeof(Cx<float>) * ne * cnt, cudaMemcpyDeviceToDevice, st));
+        generic_fft_cols(generic_cfg(P), P->ax1.dev(), P->pct_scr, cnt, st);
+        for (int i = 0; i < cnt; ++i) {
+            k_abs_keys<<<(unsigned)std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(P->pct_scr + (int64_t)i * ne, P->pct_keys, ne);
+            size_t tb = P->cub_temp_bytes;
+            cub::DeviceRadixSort::SortKeys(P->cub_temp, tb, P->pct_keys, P->pct_sorted, (long long)ne, 0, 32, st);
+            k_pick_percentile<<<1, 1, 0, st>>>(P->pct_sorted, ne, const_cast<Cx<float>*>(B.tau) + (s0 + i) * B.niter + k);
+        }
+    }
+    prof_end(P, st);
+    P3D_CUDA(cudaGetLastError());
 }
 
 struct RunCtx {
@@ -501,6 +558,7 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             B.k = k; B.last = (k == niter - 1) ? 1 : 0;
             // x_k only has to reach OUT when iteration k can be the last one executed
             B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
+            if (pr.thresh_percentile) percentile_thresholds(P, st, B, nb, k);
             launch_cols_iter(P, st, B, nb, pr.thresh_op);
             launch_rows_iter(P, st, B, nb);
         }
@@ -524,6 +582,13 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     P3D_REQUIRE(pr->thresh_model >= 0 && pr->thresh_model <= 3, P3D_ERR_NOT_IMPLEMENTED, "unsupported thresh_model %d", pr->thresh_model);
     P3D_REQUIRE(pr->version >= 0 && pr->version <= 2, P3D_ERR_BAD_ARG, "unsupported version %d", pr->version);
     if (!schedule_only) P3D_REQUIRE(mask && out, P3D_ERR_BAD_ARG, "null mask / out");
+    if (pr->thresh_percentile) {
+        P3D_REQUIRE(pr->decay_factors && pr->p_max >= 0.0 && pr->p_max <= 100.0 && pr->p_min >= 0.0 && pr->p_min <= 100.0,
+                    P3D_ERR_BAD_ARG, "Percentiles must be in the range [0, 100]");
+        P3D_REQUIRE(pr->thresh_model == P3D_MODEL_LINEAR || pr->thresh_model == P3D_MODEL_EXPONENTIAL, P3D_ERR_NOT_IMPLEMENTED,
+                    "percentile operators need a linear or exponential schedule of percentiles");
+        P3D_REQUIRE(P->precision != 64, P3D_ERR_NOT_IMPLEMENTED, "percentile operators run in the fp32 path only");
+    }
     if (n_slices == 0) return P3D_OK;
     if (spm <= 0) spm = n_slices;
     DeviceGuard guard(P->device);
@@ -546,7 +611,8 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     // i+4 hide behind the iterations of chunks i+1..i+3 even when the PCIe path is slow (8 ranks sharing
     // one host: 8-11 GB/s per direction measured; e2e at 8 GPUs 444k -> 506k slice-it/s going from 2 to 4
     // lanes, 76.6k -> 80.9k on one GPU); device-resident data need one lane.
-    const int lanes = P->n_lanes > 0 ? P->n_lanes : ((host_in || host_out) ? 4 : 1);
+    // (the percentile operators share one scratch area and sort inside the iteration loop: one lane)
+    const int lanes = pr->thresh_percentile ? 1 : (P->n_lanes > 0 ? P->n_lanes : ((host_in || host_out) ? 4 : 1));
     if ((int)P->lanes.size() < lanes) P->lanes.resize(lanes);
     const int nbuf = 1 + (host_in ? 1 : 0) + (host_out ? 1 : 0);
     for (auto& L : P->lanes) L.pending = false;
@@ -647,6 +713,9 @@ int p3d_plan_destroy(p3d_plan* P) {
     if (P->spec_tw_cols) cudaFree(P->spec_tw_cols);
     if (P->spec_tw_rows) cudaFree(P->spec_tw_rows);
     if (P->cub_temp) cudaFree(P->cub_temp);
+    if (P->pct_scr) cudaFree(P->pct_scr);
+    if (P->pct_keys) cudaFree(P->pct_keys);
+    if (P->pct_sorted) cudaFree(P->pct_sorted);
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
     delete P;
     return P3D_OK;

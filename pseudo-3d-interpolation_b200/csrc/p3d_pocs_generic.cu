@@ -85,6 +85,9 @@ void generic_cols_iter(const GenericCfg& c, const AxisDev<float>& ax1, const Ban
 void generic_rows_iter(const GenericCfg& c, const AxisDev<float>& ax2, const BandArgs<float>& A, int ns, cudaStream_t st) {
     k_rows_generic<float, 1><<<row_grid(c, ns), c.row_threads, c.row_smem, st>>>(c.geom, ax2, A);
 }
+void generic_fft_cols(const GenericCfg& c, const AxisDev<float>& ax1, Cx<float>* data, int ns, cudaStream_t st) {
+    k_fft2_cols<-1><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, data);
+}
 void generic_fft2(const GenericCfg& c, const AxisDev<float>& ax1, const AxisDev<float>& ax2, const Cx<float>* in,
                   Cx<float>* out, int ns, int inverse, cudaStream_t st) {
     const float scale = inverse ? (float)(1.0 / ((double)c.geom.n1 * (double)c.geom.n2)) : 1.0f;

@@ -15,6 +15,8 @@ void generic_rows_init(const GenericCfg& c, const AxisDev<float>& ax2, const Ban
 void generic_cols_stats(const GenericCfg& c, const AxisDev<float>& ax1, const BandArgs<float>& A, int nslices, cudaStream_t st);
 void generic_cols_iter(const GenericCfg& c, const AxisDev<float>& ax1, const BandArgs<float>& A, int nslices, int op, cudaStream_t st);
 void generic_rows_iter(const GenericCfg& c, const AxisDev<float>& ax2, const BandArgs<float>& A, int nslices, cudaStream_t st);
+// in-place forward column FFT of slices (the first half of k_cols_generic), used by the percentile operators
+void generic_fft_cols(const GenericCfg& c, const AxisDev<float>& ax1, Cx<float>* data, int nslices, cudaStream_t st);
 void generic_fft2(const GenericCfg& c, const AxisDev<float>& ax1, const AxisDev<float>& ax2, const Cx<float>* in,
                   Cx<float>* out, int nslices, int inverse, cudaStream_t st);
 

@@ -65,9 +65,10 @@ def make_params(niter=50, thresh_op="hard", thresh_model="exponential", eps=1e-9
     eps = float(eps)
     p_max = float(p_max)
     alpha = float(alpha)
+    percentile = isinstance(thresh_op, str) and thresh_op.endswith("-percentile")
+    if percentile:
+        thresh_op = thresh_op[: -len("-percentile")]
     if thresh_op not in _lib.OPS:
-        if isinstance(thresh_op, str) and thresh_op.endswith("-percentile"):
-            raise NotImplementedError(f"thresh_op={thresh_op!r}: percentile operators are not implemented on the GPU path")
         raise NotImplementedError(f"unknown threshold operator {thresh_op!r}")
     model, q = _parse_model(thresh_model)
     if decay_kind not in ("values", "factors"):
@@ -88,6 +89,14 @@ def make_params(niter=50, thresh_op="hard", thresh_model="exponential", eps=1e-9
     p.sqrt_decay = 1 if sqrt_decay else 0
     p.decay_factors = 1 if decay_kind == "factors" else 0
     p.absmax_threshold = 1 if absmax_threshold else 0
+    p.thresh_percentile = 1 if percentile else 0
+    if percentile:
+        # '<op>-percentile' (functions/POCS.py:43-58): the scheduled value is handed to np.percentile(|X|, .), which
+        # only works for real values in [0, 100], i.e. decay_kind='factors' with p_max / p_min given in percent
+        if decay_kind != "factors" or adaptive or not (0.0 <= p_max <= 100.0 and 0.0 <= p.p_min <= 100.0):
+            raise ValueError("Percentiles must be in the range [0, 100]")
+        if model not in (_lib.MODELS["linear"], _lib.MODELS["exponential"]):
+            raise NotImplementedError(f"{thresh_model} schedule with percentile operators is not implemented")
     return p
 
 

@@ -254,6 +254,10 @@ def test_full_size_config_slices_soft_fp32(p3d):
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_f64_mode_matches_reference_golden(case, golden, p3d):
     x, mask = make_input(case)
+    if case["params"]["thresh_op"].endswith("-percentile"):
+        with pytest.raises(NotImplementedError):          # the percentile operators run in the fp32 path only
+            p3d.PocsPlan(x.shape[0], x.shape[1], precision=64).run(x.astype(np.complex64), mask, **case["params"])
+        return
     n = case["name"]
     ref = golden[f"{n}__y"]
     plan = p3d.PocsPlan(x.shape[0], x.shape[1], precision=64)
@@ -332,6 +336,22 @@ def test_f64_mode_data_driven_and_schedule(p3d):
         tau = plan.schedule(x, niter=11, thresh_model=model, p_max=0.99, p_min=1e-5)[0]
         ref = orc.threshold_table(X0, 11, model, 0.99, 1e-5)
         np.testing.assert_allclose(tau, ref, rtol=1e-10, atol=1e-12 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("shape,op", [((256, 256), "soft-percentile"), ((200, 120), "garrote-percentile"), ((64, 1000), "hard-percentile")])
+def test_percentile_operators_spec_shapes(shape, op, p3d):
+    """'<op>-percentile' (functions/POCS.py:43-58) on register-resident / mixed plans, several slices per call
+    (each slice gets its own per-iteration percentile), host-buffer path."""
+    x, mask = make_input(dict(seed=31, shape=shape, keep=0.35, nwaves=5, noise=0.01))
+    x = np.stack([x, 0.3 * x, np.conj(x)]).astype(np.complex64)
+    params = dict(niter=8, thresh_op=op, thresh_model="exponential", eps=0.0, alpha=1.0, p_max=99.5, p_min=30.0, decay_kind="factors")
+    y, info = p3d.PocsPlan(*shape).run(x, mask, **params)
+    assert list(info["niterations"]) == [8, 8, 8]
+    for i in range(3):
+        ref = orc.pocs_slice(x[i].astype(np.complex128), mask, **params)
+        e = rel_l2(y[i], ref)
+        # hard: a coefficient within fp32 rounding of the percentile value may fall on either side
+        assert e <= (RTOL if not op.startswith("hard") else 2e-3), (i, e)
 
 
 def test_per_cube_masks(p3d):

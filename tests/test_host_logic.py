@@ -23,20 +23,27 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.p3d_abi_version() == 1
+    assert lib.p3d_abi_version() == 2
 
 
 def test_params_struct_layout_matches_header():
-    # 4 int32, 5 double, 4 int32 -> 16 + 40 + 16 = 72 bytes
-    assert ctypes.sizeof(_lib.PocsParams) == 72
+    # 4 int32, 5 double, 5 int32 (+ 4 bytes tail padding) -> 16 + 40 + 24 = 80 bytes
+    assert ctypes.sizeof(_lib.PocsParams) == 80
     p = pocs.make_params(niter=7, thresh_op="garrote", thresh_model="exponential-2", eps=1e-6, alpha=0.7,
                          p_max=0.9, p_min="adaptive", sqrt_decay=True)
     assert (p.niter, p.thresh_op, p.thresh_model, p.q, p.p_min_adaptive, p.sqrt_decay) == (7, 2, 1, 2.0, 1, 1)
     assert pocs.make_params(thresh_model="inverse-proportional-3").q == 3.0
     with pytest.raises(NotImplementedError):
         pocs.make_params(thresh_model="cubic")
-    with pytest.raises(NotImplementedError):
+    # percentile operators: only with decay_kind='factors' and percentiles in [0, 100] (np.percentile's own error otherwise)
+    with pytest.raises(ValueError, match="Percentiles must be in the range"):
         pocs.make_params(thresh_op="hard-percentile")
+    with pytest.raises(ValueError, match="Percentiles must be in the range"):
+        pocs.make_params(thresh_op="soft-percentile", decay_kind="factors", p_max=120.0, p_min=1.0)
+    pp = pocs.make_params(thresh_op="garrote-percentile", decay_kind="factors", p_max=99.0, p_min=1.0)
+    assert (pp.thresh_op, pp.thresh_percentile, pp.decay_factors) == (2, 1, 1)
+    with pytest.raises(NotImplementedError):
+        pocs.make_params(thresh_op="median-percentile", decay_kind="factors", p_max=99.0, p_min=1.0)
     with pytest.raises(ValueError):
         pocs.make_params(decay_kind="nope")
     with pytest.raises(TypeError):
