@@ -188,7 +188,12 @@ void install_spec(p3d_plan* P, int variant) {
         P3D_CUDA(cudaMalloc(dst, sizeof(Cx<float>) * t.size()));
         P3D_CUDA(cudaMemcpy(*dst, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
     };
-    upload(P->spec.cols_radices, &P->spec_tw_cols);
+    if (P->spec.cols_table) {
+        if (P->spec_tw_cols) { cudaFree(P->spec_tw_cols); P->spec_tw_cols = nullptr; }
+        std::vector<Cx<float>> t = P->spec.cols_table();
+        P3D_CUDA(cudaMalloc(&P->spec_tw_cols, sizeof(Cx<float>) * t.size()));
+        P3D_CUDA(cudaMemcpy(P->spec_tw_cols, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    } else upload(P->spec.cols_radices, &P->spec_tw_cols);
     upload(P->spec.rows_radices, &P->spec_tw_rows);
     P->d_mbits_words = 0;           // layout may have changed: repack on the next run
 }

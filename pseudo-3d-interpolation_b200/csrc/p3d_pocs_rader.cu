@@ -1,0 +1,238 @@
+// Column pass of the POCS iteration for a PRIME iline count P (config 3: 1201), register-resident.
+//
+// Rader's algorithm turns a length-P DFT into a cyclic convolution of length M = P - 1:
+//     X[0]      = x[0] + sum_q a[q]                      a[q] = x[g^q mod P]   (g = primitive root mod P)
+//     X[g^-m]   = x[0] + (a (*) b)[m]                     b[t] = w^(g^-t),  w = exp(-2 pi i / P)
+// and the convolution is two M-point FFTs (M = 1200 = 10 x 12 x 10, p3d_fft_mix.cuh) around a table
+// multiply by B = FFT_M(b) / M.  What makes this cheap inside the column kernel:
+//   * a column tile is loaded row by row anyway (C adjacent columns per row segment), so the input
+//     permutation x[g^q] is just the ROW INDEX of each load - no shuffle, no shared-memory gather;
+//   * sum_q a[q] is the DC output of the first FFT, and adding x[0] to every convolution output is
+//     adding it to the DC input of the inverse FFT;
+//   * the threshold is element-wise, so the spectrum is left in Rader order (position m <-> frequency
+//     g^-m): the inverse DFT  y[g^s] = Y[0] + (h (*) b2)[s],  h[m] = Y[g^-m],  b2[t] = conj(w)^(g^t)
+//     consumes it in exactly that order and produces y[g^s] in the order of the load permutation.
+// One column-iteration therefore costs four 1200-point register FFTs and two table multiplies, against
+// four 2560-point shared-memory FFTs for the generic Bluestein path.
+// Table buffer layout (Cx<float> slots): [twiddles of 10x12x10 : T + M][B : M][B2 : M][perm : M ints][kperm : M ints]
+#include "p3d_pocs_spec.cuh"
+#include "p3d_fft_mix.cuh"
+
+#include <cmath>
+#include <complex>
+#include <cstring>
+
+namespace p3d {
+
+__device__ __forceinline__ Cx<float> ldg_cx(const Cx<float>* p) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    return cmake<float>(t.x, t.y);
+}
+
+// MODE 0: statistics of X0 (+ optional store), MODE 1: iterate (threshold / filter)
+template <typename MP, int P, int C, int MINB, int MODE>
+__global__ void __launch_bounds__(MP::T* C, MINB)
+k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tab, const __grid_constant__ BandArgs<float> A, const int op) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = MP::E, T = MP::T, M = MP::N;
+    static_assert(M == P - 1, "Rader: the convolution length is P - 1");
+    const Cx<float>* __restrict__ tw = tab;
+    const Cx<float>* __restrict__ Bf = tab + (T + M);
+    const Cx<float>* __restrict__ Bi = Bf + M;
+    const int* __restrict__ perm = reinterpret_cast<const int*>(Bi + M);
+    const int* __restrict__ kperm = perm + M;
+    const int s = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    const int col = blockIdx.x * C + c;
+    const bool ok = col < G.n2;
+    Cx<float>* __restrict__ Ws = A.W + (long long)s * P * G.n2 + col;
+    ColAcc<float, C, MP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+
+    int row[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) row[e] = __ldg(perm + j + e * T);
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)row[e] * G.n2] : cmake<float>(0.f, 0.f);
+    Cx<float> dc = (ok && j == 0) ? Ws[0] : cmake<float>(0.f, 0.f);
+    Cx<float> tau = cmake<float>(0.f, 0.f);
+    if (MODE == 1) {
+        tau = A.tau[(long long)s * A.niter + A.k];
+        if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) return;
+    }
+
+    // ---- forward DFT of length P
+    MP::template fft<-1, 0, float>(v, acc, j, tw);
+    {
+        const Cx<float> x0 = dc;
+        if (j == 0) dc = cadd(x0, v[0]);                 // X[0] = x[0] + sum_q a[q]
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], ldg_cx(Bf + j + e * T));
+        if (j == 0) v[0] = cadd(v[0], x0);               // + x[0] on every convolution output
+    }
+    MP::template fft<+1, 0, float>(v, acc, j, tw);
+    // v[e] = X[kperm[j + e*T]], dc = X[0] (threads j == 0)
+
+    if (MODE == 0) {
+        unsigned long long kmax = 0ull; float ssf = 0.f; unsigned int amax = 0u, amin = 0xffffffffu;
+        Cx<float>* __restrict__ X0 = A.OUT + (long long)s * P * G.n2 + col;
+        auto account = [&](const Cx<float> x, const int frow) {
+            const unsigned long long key = lex_key(x.x, x.y);
+            kmax = key > kmax ? key : kmax;
+            const float r2 = x.x * x.x + x.y * x.y;
+            ssf += r2;
+            const unsigned int rb = __float_as_uint(sqrtf(r2));
+            amax = rb > amax ? rb : amax; amin = rb < amin ? rb : amin;
+            if (A.store_x0) X0[(long long)frow * G.n2] = x;
+        };
+        if (ok) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) account(v[e], __ldg(kperm + j + e * T));
+            if (j == 0) account(dc, 0);
+        }
+        kmax = warp_max_u64(kmax); const double ss = warp_sum((double)ssf); amax = warp_max_u32(amax); amin = warp_min_u32(amin);
+        if ((tid & 31) == 0) {
+            atomicMax(&A.stats[s].lexmax_key, kmax);
+            atomicAdd(&A.stats[s].sumsq, ss);
+            atomicMax(&A.stats[s].maxabs_bits, amax);
+            atomicMin(&A.stats[s].minabs_bits, amin);
+        }
+        return;
+    }
+
+    // ---- threshold (or kx-ky filter) in Rader order
+    const float a = tau.x, b = tau.y;
+    const float t2re = a * a - b * b, t2im = 2.f * a * b;
+    if (op == P3D_OP_HARD && !A.exact_tie) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float, false>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_HARD, float, false>(dc, a, b, t2re, t2im);
+    } else if (op == P3D_OP_HARD) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_HARD, float>(dc, a, b, t2re, t2im);
+    } else if (op == P3D_OP_SOFT) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_SOFT, float>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_SOFT, float>(dc, a, b, t2re, t2im);
+    } else if (op == P3D_OP_GARROTE) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_GARROTE, float>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_GARROTE, float>(dc, a, b, t2re, t2im);
+    } else {
+        const float* __restrict__ H = A.filt + col;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float h = ok ? __ldg(H + (long long)__ldg(kperm + j + e * T) * G.n2) : 0.f;
+            v[e] = cmake<float>(v[e].x * h, v[e].y * h);
+        }
+        const float h0 = (ok && j == 0) ? __ldg(H) : 0.f;
+        dc = cmake<float>(dc.x * h0, dc.y * h0);
+    }
+
+    // ---- inverse DFT of length P (unscaled): h[m] = Y[g^-m] is already in natural order of m
+    MP::template fft<-1, 0, float>(v, acc, j, tw);
+    {
+        const Cx<float> y0 = dc;
+        if (j == 0) dc = cadd(y0, v[0]);                 // y[0] = sum_k Y[k]
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], ldg_cx(Bi + j + e * T));
+        if (j == 0) v[0] = cadd(v[0], y0);
+    }
+    MP::template fft<+1, 0, float>(v, acc, j, tw);
+    // v[e] = y[g^(j + e*T)] = y[row[e]]
+
+    if (ok) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) Ws[(long long)row[e] * G.n2] = v[e];
+        if (j == 0) Ws[0] = dc;
+    }
+}
+
+// ---- host: tables ----------------------------------------------------------------------------------------
+static long powmod(long b, long e, long m) { long r = 1; b %= m; while (e > 0) { if (e & 1) r = r * b % m; b = b * b % m; e >>= 1; } return r; }
+static int primitive_root(int p) {
+    std::vector<int> factors;
+    int phi = p - 1, n = phi;
+    for (int f = 2; f * f <= n; ++f) if (n % f == 0) { factors.push_back(f); while (n % f == 0) n /= f; }
+    if (n > 1) factors.push_back(n);
+    for (int g = 2; g < p; ++g) {
+        bool ok = true;
+        for (int f : factors) if (powmod(g, phi / f, p) == 1) { ok = false; break; }
+        if (ok) return g;
+    }
+    return -1;
+}
+
+template <typename MP, int P> static std::vector<Cx<float>> rader_tables() {
+    constexpr int M = P - 1;
+    int rad[3]; MP::radices(rad);
+    std::vector<Cx<float>> t = spec_twiddle_table(std::vector<int>(rad, rad + 3));
+    t.resize((size_t)MP::T + M);                                    // exact size of the twiddle section
+    const int g = primitive_root(P);
+    const long ginv = powmod(g, P - 2, P);
+    std::vector<int> perm(M), kperm(M);
+    for (int q = 0; q < M; ++q) { perm[q] = (int)powmod(g, q, P); kperm[q] = (int)powmod(ginv, q, P); }
+    typedef std::complex<double> cd;
+    std::vector<cd> bf(M), bi(M);
+    for (int q = 0; q < M; ++q) {
+        bf[q] = std::polar(1.0, -2.0 * M_PI * (double)kperm[q] / (double)P);      // w^(g^-q)
+        bi[q] = std::polar(1.0, +2.0 * M_PI * (double)perm[q] / (double)P);       // conj(w)^(g^q)
+    }
+    // M-point DFTs of the two kernels (once per plan: M^2 = 1.44 M complex multiplies), scaled by 1/M
+    std::vector<cd> wM(M);
+    for (int k = 0; k < M; ++k) wM[k] = std::polar(1.0, -2.0 * M_PI * (double)k / (double)M);
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<cd>& src = pass == 0 ? bf : bi;
+        for (int k = 0; k < M; ++k) {
+            cd acc(0, 0);
+            for (int q = 0; q < M; ++q) acc += src[q] * wM[(int)(((long)k * q) % M)];
+            acc /= (double)M;
+            t.push_back(cmake<float>((float)acc.real(), (float)acc.imag()));
+        }
+    }
+    const size_t int_slots = (size_t)M;                            // 2 * M ints = M Cx<float> slots
+    const size_t base = t.size();
+    t.resize(base + int_slots);
+    int* ip = reinterpret_cast<int*>(t.data() + base);
+    memcpy(ip, perm.data(), sizeof(int) * M);
+    memcpy(ip + M, kperm.data(), sizeof(int) * M);
+    return t;
+}
+
+template <typename MP, int P, int C, int MINB, int MODE>
+static void launch_rader(const PocsGeom& G, const Cx<float>* tab, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * MP::LINE * C * sizeof(Cx<float>);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_cols_rader<MP, P, C, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid((G.n2 + C - 1) / C, ns);
+    k_cols_rader<MP, P, C, MINB, MODE><<<grid, MP::T * C, smem, st>>>(G, tab, A, op);
+}
+template <typename MP, int P, int C, int MINB>
+static void launch_rader_stats(const PocsGeom& G, const Cx<float>* tab, const BandArgs<float>& A, int ns, cudaStream_t st) {
+    launch_rader<MP, P, C, MINB, 0>(G, tab, A, ns, 0, st);
+}
+
+typedef MixPlan3<1200, 10, 12> MP1200;
+
+void rader_register_cols(SpecKernels& k, int n_iline, int variant) {
+    if (n_iline != 1201) return;
+    if (variant == 1) {
+        k.cols_iter = launch_rader<MP1200, 1201, 2, 4, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 2, 4>;
+        k.cols_name = "rader<1201,10x12x10,C2,4cta>";
+    } else if (variant == 2) {
+        k.cols_iter = launch_rader<MP1200, 1201, 4, 1, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 4, 1>;
+        k.cols_name = "rader<1201,10x12x10,C4,1cta>";
+    } else {
+        k.cols_iter = launch_rader<MP1200, 1201, 4, 2, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 4, 2>;
+        k.cols_name = "rader<1201,10x12x10,C4,2cta>";
+    }
+    k.cols_radices = {10, 12, 10};
+    k.cols_table = rader_tables<MP1200, 1201>;
+}
+
+}  // namespace p3d

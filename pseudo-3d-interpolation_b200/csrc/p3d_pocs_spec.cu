@@ -7,6 +7,7 @@
 //   rows_iter:  thread (j, rr) of a tile of RB rows holds columns j + e*T of row rr.
 //               load -> IFFT -> x = alpha*d + (1-alpha*m)*y/(N1 N2) -> sum|x| -> [OUT] -> FFT -> store.
 #include "p3d_pocs_spec.cuh"
+#include "p3d_fft_mix.cuh"
 #include "p3d_fft_reg.cuh"
 
 #include <cmath>
@@ -367,6 +368,7 @@ typedef LinePlan<2000, 10, 10, 10, 10, 2> LP2000;
 typedef LinePlan<2000, 20, 20, 10, 10> LP2000E20;
 typedef LinePlan<256, 16, 16, 16> LP256;
 typedef LinePlan<200, 20, 10, 20> LP200;
+typedef MixPlan3<847, 11, 7> MP847;          // 11 x 7 x 11 (config 3's xline axis)
 
 #define P3D_COLS(LP, C, MINB, NAME) do { k.cols_iter = launch_cols<LP, C, MINB>; k.cols_stats = launch_cols_stats<LP, C, MINB>; \
                                          k.cols_name = NAME; k.cols_radices = radices_of<LP>(); } while (0)
@@ -394,7 +396,7 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             break;
         case 256:  P3D_COLS(LP256, 16, 3, "spec<256,E16,16x16,C16>"); break;
         case 200:  P3D_COLS(LP200, 16, 4, "spec<200,E20,10x20,C16>"); break;
-        default: break;
+        default: rader_register_cols(k, n_iline, variant); break;
     }
     switch (n_xline) {      // row transforms have the length of the xline axis
         case 1000:
@@ -417,6 +419,11 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             if (variant == 1) P3D_ROWS(LP256, 16, 3, "spec<256,E16,16x16,RB16>");
             else if (variant == 2) P3D_ROWS(LP256, 4, 10, "spec<256,E16,16x16,RB4>");
             else P3D_ROWS(LP256, 8, 5, "spec<256,E16,16x16,RB8>");
+            break;
+        case 847:
+            if (variant == 1) P3D_ROWS(MP847, 2, 4, "mix<847,11x7x11,RB2,4cta>");
+            else if (variant == 2) P3D_ROWS(MP847, 4, 3, "mix<847,11x7x11,RB4,3cta>");
+            else P3D_ROWS(MP847, 3, 4, "mix<847,11x7x11,RB3,4cta>");
             break;
         case 200:
             if (variant == 1) P3D_ROWS(LP200, 16, 4, "spec<200,E20,10x20,RB16>");

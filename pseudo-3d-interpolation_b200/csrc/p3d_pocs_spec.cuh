@@ -21,7 +21,12 @@ struct SpecKernels {
     const char* rows_name = "generic";
     std::vector<int> cols_radices, rows_radices;   // for the twiddle tables
     int rows_T = 0;                                 // threads per row line (packed-mask layout)
+    // optional: builder of the column kernels' whole table buffer (twiddles + algorithm tables, e.g. Rader's)
+    std::vector<Cx<float>> (*cols_table)() = nullptr;
 };
+
+// prime iline counts handled by Rader's algorithm (p3d_pocs_rader.cu); no-op for other lengths
+void rader_register_cols(SpecKernels& k, int n_iline, int variant);
 
 SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant = 0);
 
