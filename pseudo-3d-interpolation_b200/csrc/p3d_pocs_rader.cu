@@ -218,6 +218,7 @@ static void launch_rader_stats(const PocsGeom& G, const Cx<float>* tab, const Ba
 }
 
 typedef MixPlan3<1200, 10, 12> MP1200;
+typedef MixPlan3<1200, 20, 3> MP1200E20;
 
 void rader_register_cols(SpecKernels& k, int n_iline, int variant) {
     if (n_iline != 1201) return;
@@ -227,7 +228,19 @@ void rader_register_cols(SpecKernels& k, int n_iline, int variant) {
     } else if (variant == 2) {
         k.cols_iter = launch_rader<MP1200, 1201, 4, 1, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 4, 1>;
         k.cols_name = "rader<1201,10x12x10,C4,1cta>";
-    } else {
+    } else if (variant == 0) {
+        k.cols_iter = launch_rader<MP1200E20, 1201, 4, 2, 1>; k.cols_stats = launch_rader_stats<MP1200E20, 1201, 4, 2>;
+        k.cols_name = "rader<1201,20x3x20,C4,2cta>";
+        k.cols_radices = {20, 3, 20};
+        k.cols_table = rader_tables<MP1200E20, 1201>;
+        return;
+    } else if (variant == 4) {
+        k.cols_iter = launch_rader<MP1200E20, 1201, 8, 1, 1>; k.cols_stats = launch_rader_stats<MP1200E20, 1201, 8, 1>;
+        k.cols_name = "rader<1201,20x3x20,C8,1cta>";
+        k.cols_radices = {20, 3, 20};
+        k.cols_table = rader_tables<MP1200E20, 1201>;
+        return;
+    } else {   // variant 3
         k.cols_iter = launch_rader<MP1200, 1201, 4, 2, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 4, 2>;
         k.cols_name = "rader<1201,10x12x10,C4,2cta>";
     }
