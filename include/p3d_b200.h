@@ -130,6 +130,11 @@ int p3d_time_ifft(int device, const void* x, int x_mem, float* out, int out_mem,
                   int64_t nfft, int64_t nt_out, int64_t n_traces, double dt, double t0,
                   int compute_real, int ascending);
 
+/* Amplitude envelope along the time axis: env = |x + i Hilbert(x)|, the arithmetic of functions/signal.py:672-690
+ * (scipy.signal.hilbert + abs) used by step 11 (cube_preprocessing_3D.py:341-353) to make the `env` variable.
+ *   x, out : (nt, n_traces) float32, time-major; any nt (register-resident pipeline for 512/1024/2048/4096) */
+int p3d_time_envelope(int device, const float* x, int x_mem, float* out, int out_mem, int64_t nt, int64_t n_traces);
+
 /* Device time (CUDA events) spent in the kernels of this thread's last p3d_time_fft / p3d_time_ifft
  * call (0 when the call used the generic direct kernels). */
 int p3d_time_last_kernel_ms(double* ms);

@@ -139,3 +139,21 @@ def rescale_envelope(x):
     if amin == amax:
         return x
     return 0 + (x - amin) * ((1 - 0) / (amax - amin))
+
+
+def envelope(x, axis=-1):
+    """Amplitude envelope |x + i Hilbert(x)| along ``axis`` in float64: the reference's ``functions/signal.py:672-690``
+    (``scipy.signal.hilbert`` = one-sided spectrum weights 1, 2, ..., 2, (1 at Nyquist for even N), 0, ... then
+    ``abs``), restated with numpy FFTs.  Pinned by tests/golden/reference_envelope.npz (oracle/make_golden_envelope.py)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[axis]
+    h = np.zeros(n)
+    if n % 2 == 0:
+        h[0] = h[n // 2] = 1.0
+        h[1:n // 2] = 2.0
+    else:
+        h[0] = 1.0
+        h[1:(n + 1) // 2] = 2.0
+    shape = [1] * x.ndim
+    shape[axis] = n
+    return np.abs(np.fft.ifft(np.fft.fft(x, axis=axis) * h.reshape(shape), axis=axis))

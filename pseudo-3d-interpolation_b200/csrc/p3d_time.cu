@@ -388,6 +388,90 @@ k_time_inv_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Amplitude envelope |x + i H[x]| along the time axis (functions/signal.py:672-690: scipy.signal.hilbert,
+// abs, cast to the input dtype).  Two real traces are packed into one complex line z = a + i b; since
+// H[a], H[b] are real, ONE inverse transform of  -i sgn(k) FFT(z)[k] / N  returns H[a] + i H[b]
+// (sgn = +1 below Nyquist, -1 above, 0 at DC and Nyquist: scipy's one-sided weights 1, 2, ..., 2, 1, 0, ...).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Cx<float> hilbert_weight(Cx<float> z, int k, int N, float inv_n) {
+    // -i * sgn(k) * z / N
+    const bool zero = (k == 0) || (2 * k == N);
+    const float sg = zero ? 0.f : ((2 * k < N) ? inv_n : -inv_n);
+    return cmake<float>(sg * z.y, -sg * z.x);
+}
+
+// generic direct kernel (any record length): x (nt, ntr) -> env (nt, ntr)
+__global__ void k_time_env(const __grid_constant__ TimeGeom G, const __grid_constant__ AxisDev<float> ax,
+                           const float* __restrict__ x, float* __restrict__ env) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    Cx<float>* bufA = reinterpret_cast<Cx<float>*>(smem_raw);
+    Cx<float>* bufB = bufA + (size_t)ax.L * G.C;
+    const long long tr0 = (long long)blockIdx.x * 2 * G.C;
+    const int ntr_tile = (int)min((long long)2 * G.C, G.ntr - tr0);
+    const int nc = (ntr_tile + 1) / 2;
+    const int N = G.nfft;
+    const int tot = N * nc;
+    for (int w = tid; w < tot; w += nth) {
+        const int n = w / nc, c = w - n * nc;
+        const long long base = (long long)n * G.ntr + tr0 + 2 * c;
+        const float a = x[base];
+        const float b = (2 * c + 1 < ntr_tile) ? x[base + 1] : 0.f;
+        bufA[n * G.C + c] = cmake<float>(a, b);
+    }
+    __syncthreads();
+    TileGeom tg; tg.nlines = nc; tg.line_stride = 1; tg.elem_stride = G.C; tg.line_fastest = 1;
+    Cx<float>* Z = line_fft<-1, float>(bufA, bufB, tg, ax, tid, nth);
+    Cx<float>* other = (Z == bufA) ? bufB : bufA;
+    const float inv_n = 1.f / (float)N;
+    for (int w = tid; w < tot; w += nth) {
+        const int k = w / nc, c = w - k * nc;
+        Z[k * G.C + c] = hilbert_weight(Z[k * G.C + c], k, N, inv_n);
+    }
+    __syncthreads();
+    Cx<float>* Hx = line_fft<+1, float>(Z, other, tg, ax, tid, nth);
+    for (int w = tid; w < tot; w += nth) {
+        const int n = w / nc, c = w - n * nc;
+        const long long base = (long long)n * G.ntr + tr0 + 2 * c;
+        const Cx<float> h = Hx[n * G.C + c];
+        const float a = x[base];
+        env[base] = sqrtf(a * a + h.x * h.x);
+        if (2 * c + 1 < ntr_tile) { const float b = x[base + 1]; env[base + 1] = sqrtf(b * b + h.y * h.y); }
+    }
+}
+
+// trace-major register-resident version: xt (ntr_chunk, nt) -> et (ntr_chunk, nt); RB trace PAIRS per CTA
+template <typename LP, int RB>
+__global__ void __launch_bounds__(LP::T* RB, 2)
+k_time_env_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict__ tw, const float* __restrict__ xt,
+                float* __restrict__ et, const long long ntr_chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    const int tid = threadIdx.x;
+    const int j = tid % T, rr = tid / T;
+    const long long ta = ((long long)blockIdx.x * RB + rr) * 2, tb = ta + 1;
+    const bool oka = ta < ntr_chunk, okb = tb < ntr_chunk;
+    RowAcc<float, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
+    const float* __restrict__ pa = xt + ta * N + j;
+    const float* __restrict__ pb = xt + tb * N + j;
+    Cx<float> v[E], x0[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { x0[e] = cmake<float>(oka ? pa[e * T] : 0.f, okb ? pb[e * T] : 0.f); v[e] = x0[e]; }
+    LP::template fft<-1, 0, float>(v, acc, j, tw);
+    const float inv_n = 1.f / (float)N;
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = hilbert_weight(v[e], j + e * T, N, inv_n);
+    LP::template fft<+1, (LP::NEXCH & 1), float>(v, acc, j, tw);
+    float* __restrict__ oa = et + ta * N + j;
+    float* __restrict__ ob = et + tb * N + j;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if (oka) oa[e * T] = sqrtf(x0[e].x * x0[e].x + v[e].x * v[e].x);
+        if (okb) ob[e * T] = sqrtf(x0[e].y * x0[e].y + v[e].y * v[e].y);
+    }
+}
+
 // device time of the kernels of the last p3d_time_fft / p3d_time_ifft call of this thread
 static thread_local double g_last_kernel_ms = 0.0;
 
@@ -497,6 +581,42 @@ bool try_time_spec(const TimeGeom& G, const void* din, void* dout, const Cx<floa
     }
 }
 
+template <typename LP, int RB>
+bool launch_env_pipeline(const TimeGeom& G, const float* din, float* dout, size_t smem_optin) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
+    if (smem > smem_optin - 1024) return false;
+    std::vector<int> rad(LP::NPASS);
+    LP::radices(rad.data());
+    std::vector<Cx<float>> t = spec_twiddle_table(rad);
+    // the two trace-major intermediates (input and envelope, nt floats each) of a chunk stay L2 resident
+    long long chunk = (long long)((size_t)72 * 1024 * 1024 / ((size_t)G.nt * 2 * sizeof(float)));
+    chunk = std::max<long long>(256, (chunk / 64) * 64);
+    chunk = std::min<long long>(chunk, ((G.ntr + 1) / 2) * 2);
+    Cx<float>* d_tw = nullptr; float* tmp_a = nullptr; Cx<float>* tmp_b = nullptr;
+    struct Free { void* p; cudaEvent_t e0, e1; ~Free() { if (p) cudaFree(p); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); } } fr{nullptr, nullptr, nullptr};
+    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size())); fr.p = d_tw;
+    int dev = 0; P3D_CUDA(cudaGetDevice(&dev));
+    scratch_get(dev, (size_t)G.nt * chunk, ((size_t)G.nt * chunk + 1) / 2, &tmp_a, &tmp_b);
+    float* tmp_e = reinterpret_cast<float*>(tmp_b);
+    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    P3D_CUDA(cudaEventCreate(&fr.e0)); P3D_CUDA(cudaEventCreate(&fr.e1));
+    P3D_CUDA(cudaEventRecord(fr.e0, 0));
+    P3D_CUDA(cudaFuncSetAttribute(k_time_env_rows<LP, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 tb(32, 8);
+    for (long long c0 = 0; c0 < G.ntr; c0 += chunk) {
+        const long long nc = std::min<long long>(chunk, G.ntr - c0);
+        const unsigned ctas = (unsigned)((nc + 2 * RB - 1) / (2 * RB));
+        k_transpose<float, false><<<dim3((unsigned)((nc + 31) / 32), (unsigned)((G.nt + 31) / 32)), tb>>>(din + c0, tmp_a, G.nt, nc, G.ntr, G.nt);
+        k_time_env_rows<LP, RB><<<ctas, LP::T * RB, smem>>>(G, d_tw, tmp_a, tmp_e, nc);
+        k_transpose<float, true><<<dim3((unsigned)((nc + 31) / 32), (unsigned)((G.nt + 31) / 32)), tb>>>(tmp_e, dout + c0, nc, G.nt, G.nt, G.ntr);
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaEventRecord(fr.e1, 0));
+    P3D_CUDA(cudaDeviceSynchronize());
+    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.e0, fr.e1); g_last_kernel_ms = ms; }
+    return true;
+}
+
 struct DeviceGuard {
     int prev = 0;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
@@ -588,6 +708,49 @@ int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int6
     return P3D_OK;
 }
 
+int envelope_impl(int device, const float* x, int x_mem, float* out, int out_mem, int64_t nt, int64_t ntr) {
+    P3D_REQUIRE(x && out, P3D_ERR_BAD_ARG, "null argument");
+    P3D_REQUIRE(nt >= 1 && ntr >= 1, P3D_ERR_BAD_ARG, "need nt >= 1 and n_traces >= 1");
+    int ndev = 0; P3D_CUDA(cudaGetDeviceCount(&ndev));
+    P3D_REQUIRE(device >= 0 && device < ndev, P3D_ERR_BAD_ARG, "device %d out of range", device);
+    DeviceGuard guard(device);
+    int optin = 0; P3D_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    g_last_kernel_ms = 0.0;
+    AxisPlan ax;
+    struct Cleanup { AxisPlan* a; void* p[2]; ~Cleanup() { a->release(); for (void* q : p) if (q) cudaFree(q); } } cl{&ax, {nullptr, nullptr}};
+    const size_t bytes = sizeof(float) * nt * ntr;
+    const float* din = x; float* dout = out;
+    if (x_mem == P3D_MEM_HOST) { void* p = nullptr; P3D_CUDA(cudaMalloc(&p, bytes)); cl.p[0] = p; P3D_CUDA(cudaMemcpy(p, x, bytes, cudaMemcpyHostToDevice)); din = (const float*)p; }
+    if (out_mem == P3D_MEM_HOST) { void* p = nullptr; P3D_CUDA(cudaMalloc(&p, bytes)); cl.p[1] = p; dout = (float*)p; }
+    TimeGeom G; G.nt = nt; G.nf = nt; G.ntr = ntr; G.nfft = (int)nt; G.C = 1; G.compute_real = 0; G.ascending = 0;
+    static const bool no_spec = getenv("P3D_TIME_GENERIC") != nullptr;
+    bool done = false;
+    if (!no_spec) {
+        switch (nt) {
+            case 512:  done = launch_env_pipeline<TP512, 4>(G, din, dout, (size_t)optin); break;
+            case 1024: done = launch_env_pipeline<TP1024, 4>(G, din, dout, (size_t)optin); break;
+            case 2048: done = launch_env_pipeline<TP2048, 2>(G, din, dout, (size_t)optin); break;
+            case 4096: done = launch_env_pipeline<TP4096, 1>(G, din, dout, (size_t)optin); break;
+            default: break;
+        }
+    }
+    if (!done) {
+        ax.build((int)nt);
+        const int C = choose_cols(ax.L, (size_t)optin);
+        const size_t smem = (size_t)2 * ax.L * C * sizeof(Cx<float>);
+        P3D_REQUIRE(smem <= (size_t)optin, P3D_ERR_NOT_IMPLEMENTED, "time axis of %lld samples does not fit in shared memory", (long long)nt);
+        G.C = C;
+        const long long tiles = (ntr + 2 * C - 1) / (2 * C);
+        P3D_REQUIRE(tiles < 2147483647LL, P3D_ERR_BAD_ARG, "too many traces");
+        P3D_CUDA(cudaFuncSetAttribute(k_time_env, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        k_time_env<<<(unsigned)tiles, 512, smem>>>(G, ax.dev(), din, dout);
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaDeviceSynchronize());
+    if (out_mem == P3D_MEM_HOST) P3D_CUDA(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    return P3D_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -603,6 +766,11 @@ int p3d_time_fft(int device, const float* x, int x_mem, void* out, int out_mem, 
 int p3d_time_ifft(int device, const void* x, int x_mem, float* out, int out_mem, int64_t nfft, int64_t nt_out,
                   int64_t n_traces, double dt, double t0, int compute_real, int ascending) {
     try { return time_impl(device, x, x_mem, out, out_mem, nt_out, nfft, n_traces, dt, t0, compute_real, ascending, nullptr, true); }
+    catch (const P3dFail& f) { return f.code; }
+}
+
+int p3d_time_envelope(int device, const float* x, int x_mem, float* out, int out_mem, int64_t nt, int64_t n_traces) {
+    try { return envelope_impl(device, x, x_mem, out, out_mem, nt, n_traces); }
     catch (const P3dFail& f) { return f.code; }
 }
 

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["freq_axis", "time_fft", "time_ifft", "freq_filter_window", "freq_filter_keep", "rescale_envelope"]
+__all__ = ["freq_axis", "time_fft", "time_ifft", "freq_filter_window", "freq_filter_keep", "rescale_envelope", "envelope"]
 
 
 def freq_axis(nfft, dt, compute_real, ascending=False):
@@ -126,3 +126,20 @@ def rescale_envelope(x):
     if lo == hi:
         return x
     return (x - lo) * (1.0 / (hi - lo))
+
+
+def envelope(signal, axis=-1, device=0):
+    """Amplitude envelope of a trace (1D), section (2D) or cube (3D) along ``axis`` via the Hilbert transform, on
+    the GPU: same signature and result dtype as the reference's ``functions/signal.py:672-690`` (step 11's ``env``
+    variable, cube_preprocessing_3D.py:341-353).  The kernel works on a time-major ``(nt, n_traces)`` view, so
+    ``axis=0`` of a ``(twt, iline, xline)`` cube needs no copy."""
+    _lib.require_gpu()
+    signal = np.asarray(signal)
+    x = np.moveaxis(signal, axis, 0)
+    lead = x.shape
+    x2 = np.ascontiguousarray(x.reshape(lead[0], -1), dtype=np.float32)
+    out = np.empty_like(x2)
+    if x2.size:
+        _lib.check(_lib.load().p3d_time_envelope(int(device), _lib.ptr(x2), _lib.MEM_HOST, _lib.ptr(out), _lib.MEM_HOST,
+                                                 x2.shape[0], x2.shape[1]))
+    return np.moveaxis(out.reshape(lead), 0, axis).astype(signal.dtype, copy=False)
