@@ -386,6 +386,7 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else if (variant == 8) P3D_COLS(LP1000E20, 8, 1, "spec<1000,E20,10x10x10,C8,1cta>");
             else if (variant == 2) { k.cols_iter = launch_cols<LP1000, 4, 2, true>; k.cols_name = "spec<1000,E10,10x10x10,C4,2cta,l2prefetch>"; k.cols_radices = radices_of<LP1000>(); }
             else if (variant == 4) P3D_COLS(LP1000, 2, 4, "spec<1000,E10,10x10x10,C2,4cta>");
+            else if (variant == 12) P3D_COLS(LP1000E20, 4, 3, "spec<1000,E20,10x10x10,C4,3cta>");
             else              P3D_COLS(LP1000E20, 4, 2, "spec<1000,E20,10x10x10,C4,2cta>");
             break;
         case 2000:

@@ -232,6 +232,30 @@ def test_full_size_config_slices(p3d):
         assert np.array_equal(y[:, obs], d[:, obs])
 
 
+@pytest.mark.parametrize("cfg,ids,niter", [(1, [20, 100, 200], 50), (2, [300, 700], 25), (3, [500], 12), (4, [900], 8), (5, [40, 400, 333], 30)])
+def test_full_size_properties_all_configs(cfg, ids, niter, p3d):
+    """Size-independent properties at the real slice sizes of all five BASELINE configs (each config's own operator,
+    schedule and alpha; iteration counts shortened where a slice is 4 M points):
+      * scale equivariance, bit for bit: POCS(2 x) == 2 POCS(x) (thresholds are p * z(x); powers of two are exact in fp32);
+      * batch independence, bit for bit: a slice's result does not depend on which other slices share the call;
+      * observed traces reproduced exactly when alpha = 1, the result is finite, unobserved traces get filled."""
+    from pseudo_3d_interpolation_b200 import synth
+    d, fold, c = synth.sparse_freq_slices(cfg, slice_ids=ids)
+    params = dict(niter=niter, thresh_op=c["thresh_op"], thresh_model=c["thresh_model"], eps=0.0, alpha=c["alpha"], p_max=0.99, p_min=1e-5)
+    mask = orc.mask_from_fold(fold)
+    plan = p3d.PocsPlan(c["n_il"], c["n_xl"])
+    y, info = plan.run(d, mask, **params)
+    assert list(info["niterations"]) == [niter] * len(ids) and np.isfinite(y.view(np.float32)).all()
+    y2, _ = plan.run((2 * d).astype(np.complex64), mask, **params)
+    assert np.array_equal(y2, 2 * y)
+    y1, _ = plan.run(d[-1:], mask, **params)
+    assert np.array_equal(y1[0], y[-1])
+    obs = mask == 1
+    if c["alpha"] == 1.0:
+        assert np.array_equal(y[:, obs], d[:, obs])
+    assert np.abs(y[:, ~obs]).max() > 0
+
+
 def test_full_size_config_slices_soft_fp32(p3d):
     """Soft operator, same slices, fp32 path.  With the reference's complex tau (Q1) even the
     soft and garrote operators jump at |X| = Re(tau): just below the factor is clipped to 0, at
