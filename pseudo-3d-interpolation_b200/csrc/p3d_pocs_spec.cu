@@ -393,6 +393,7 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             if (variant == 4) P3D_COLS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,C2,2cta>");
             else if (variant == 5) P3D_COLS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4>");
             else if (variant == 6) P3D_COLS(LP2000E20, 4, 2, "spec<2000,E20,20x10x10,C4,2cta>");
+            else if (variant == 7) P3D_COLS(LP2000E20, 2, 2, "spec<2000,E20,20x10x10,C2,2cta>");
             else              P3D_COLS(LP2000E20, 4, 1, "spec<2000,E20,20x10x10,C4,1cta>");
             break;
         case 256:  P3D_COLS(LP256, 16, 3, "spec<256,E16,16x16,C16>"); break;

@@ -585,3 +585,10 @@ def test_edge_many_small_cubes_with_own_masks_and_early_exit(p3d):
         assert abs(int(info["niterations"][i]) - oi["niterations"]) <= 1
         if int(info["niterations"][i]) == oi["niterations"]:
             assert rel_l2(y[i], ref) <= RTOL, (i, rel_l2(y[i], ref))
+
+
+def test_run_to_run_determinism_all_kernel_families():
+    """every kernel family (register plans, mixed radix + Rader, generic + Bluestein, percentile, float64, kx-ky
+    filter, envelope, time axis) repeated on the same input: bit-identical results (tools/sanitize_cases.py)."""
+    import runpy
+    runpy.run_path(os.path.join(ROOT, "tools", "sanitize_cases.py"), run_name="__main__")
