@@ -587,8 +587,11 @@ def test_edge_many_small_cubes_with_own_masks_and_early_exit(p3d):
             assert rel_l2(y[i], ref) <= RTOL, (i, rel_l2(y[i], ref))
 
 
+@pytest.mark.gpu
 def test_run_to_run_determinism_all_kernel_families():
     """every kernel family (register plans, mixed radix + Rader, generic + Bluestein, percentile, float64, kx-ky
     filter, envelope, time axis) repeated on the same input: bit-identical results (tools/sanitize_cases.py)."""
+    import os
     import runpy
-    runpy.run_path(os.path.join(ROOT, "tools", "sanitize_cases.py"), run_name="__main__")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runpy.run_path(os.path.join(root, "tools", "sanitize_cases.py"), run_name="__main__")
