@@ -72,7 +72,13 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
     static constexpr int TT = N / E;          // threads per line
     static constexpr int Q = E / R;           // butterflies per thread in this pass
     static constexpr int B = Ns * R;          // Stockham block of this pass
-    static constexpr int DELTA = exch_delta(Ns, R);
+    // First exchange of a ROW line (unit stride) with a block of B = R positions per thread, B % 4 == 2 (radix 10):
+    // no padding and 16-byte stores.  Eight lanes of a 128-bit store then start 2B words apart = 4, 12, 20, 28
+    // (mod 32) -> conflict-free, and the reads are consecutive 8-byte words -> conflict-free as well; the padded
+    // layout (DELTA = 1, 8-byte stores) costs the reads a 2-way conflict per half-warp (ncu: 832 k instead of
+    // 448 k wavefronts per load instruction).
+    static constexpr bool VEC1 = (Ns == 1) && (Acc::STRIDE == 1) && (R % 4 == 2) && (sizeof(T) == 4) && (sizeof...(Rest) > 0);
+    static constexpr int DELTA = VEC1 ? 0 : exch_delta(Ns, R);
     static_assert(E % R == 0, "every radix must divide the elements per thread");
     static_assert(N % (Ns * R) == 0, "radix sequence does not multiply to N");
 
@@ -117,8 +123,17 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 Cx<T>* w = line + wbase[q] * S;
+                if constexpr (VEC1) {
+                    float4* w4 = reinterpret_cast<float4*>(w);
 #pragma unroll
-                for (int r = 0; r < R; ++r) w[(r * Ns) * S] = v[q + r * Q];
+                    for (int r = 0; r < R; r += 2) {
+                        const Cx<T> a = v[q + r * Q], b = v[q + (r + 1) * Q];
+                        w4[r / 2] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) w[(r * Ns) * S] = v[q + r * Q];
+                }
             }
             acc.sync();
             if constexpr (TT % B == 0) {

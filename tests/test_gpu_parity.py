@@ -401,8 +401,12 @@ def test_config3_plans_match_generic_and_oracle(shape, op, model, alpha, version
     # path that flips one at garrote / adaptive / (1201, 48), 2.2e-3 off the oracle; tools/diag_c3.py): loose bound
     assert rel_l2(y, yg) <= max(5e-3, tol), rel_l2(y, yg)
     for i in range(2):
-        ref = orc.pocs_slice(x[i].astype(np.complex128), mask, version=version, **params)
-        assert rel_l2(y[i], ref) <= tol, (i, rel_l2(y[i], ref))
+        oinfo = {}
+        ref = orc.pocs_slice(x[i].astype(np.complex128), mask, version=version, info=oinfo, **params)
+        # with eps > 0 the stop decision (cost < eps, fp32 sums) may fall one iteration apart from the float64
+        # oracle's, and a complex tau makes even the soft operator jump at |X| = Re(tau): flip bound there
+        t = tol if (eps == 0.0 and oinfo["niterations"] == info["niterations"][i]) else max(tol, 2e-3)
+        assert rel_l2(y[i], ref) <= t, (i, rel_l2(y[i], ref), oinfo["niterations"], info["niterations"][i])
     if alpha == 1.0 and version == "regular":
         obs = mask == 1
         assert np.array_equal(y[:, obs], x[:, obs])
