@@ -20,6 +20,13 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // should already be on their way when its CTA starts
 constexpr int P3D_PREFETCH_DISTANCE = 296;
 
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_f(double v) { return warp_sum(v); }
+
 // ---- column kernel ---------------------------------------------------------------------------------
 template <typename F, typename LP, int C, int MINB, bool PF>
 __global__ void __launch_bounds__(LP::T* C, MINB)
@@ -147,7 +154,9 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
             v[e] = x;
         }
     }
-    double dp = warp_sum((double)part);
+    // warp level in the working precision (a warp holds 32 E non-negative terms: float is exact enough for a sum
+    // that is compared at 1e-5 relative), rows and slices in double
+    double dp = (double)warp_sum_f(part);
     if ((tid & 31) == 0) red_s[tid >> 5] = dp;
     __syncthreads();
     if (tid < 32) {
