@@ -13,26 +13,27 @@
 // Exchange layout: as in p3d_fft_reg.cuh, position pos written by the pass with Stockham block
 // B = Ns*R is stored at pos + (pos / B) * DELTA (bank spreading); all addresses split into a
 // per-thread base plus compile-time offsets.
-// Twiddles: the [k][R] tables of spec_twiddle_table({Ra, Rb, Ra}) (pass 2 at offset 0, pass 3 at Ra*Rb).
+// Twiddles: the tables of spec_twiddle_table({Ra, Rb, Ra}) (pass 2 at offset 0, pass 3 at Ra*Rb; layout: tw_index).
 #pragma once
 #include "p3d_fft_reg.cuh"
 
 namespace p3d {
 
-template <int DIR, int R, typename T>
-__device__ __forceinline__ void mix_twiddle(Cx<T> (&x)[R], const Cx<T>* __restrict__ trow) {
+// factors W^{r k}, r = 1 .. R-1, of the pass (Ns, R) for this thread's k; table layout: tw_index (p3d_fft_reg.cuh)
+template <int DIR, int R, int Ns, typename T>
+__device__ __forceinline__ void mix_twiddle(Cx<T> (&x)[R], const Cx<T>* __restrict__ tab, const int k) {
     if constexpr (R % 2 == 0 && sizeof(T) == 4) {
-        const float4* t4 = reinterpret_cast<const float4*>(trow);
+        const float4* t4 = reinterpret_cast<const float4*>(tab) + k;
 #pragma unroll
         for (int r2 = 0; r2 < R / 2; ++r2) {
-            const float4 w = __ldg(t4 + r2);
+            const float4 w = __ldg(t4 + r2 * Ns);
             if (r2 > 0) x[2 * r2] = (DIR < 0) ? cmul(x[2 * r2], cmake<T>(w.x, w.y)) : cmulc(x[2 * r2], cmake<T>(w.x, w.y));
             x[2 * r2 + 1] = (DIR < 0) ? cmul(x[2 * r2 + 1], cmake<T>(w.z, w.w)) : cmulc(x[2 * r2 + 1], cmake<T>(w.z, w.w));
         }
     } else {
 #pragma unroll
         for (int r = 1; r < R; ++r) {
-            const Cx<T> w = trow[r];
+            const Cx<T> w = tab[tw_index(R, Ns, r, 0) + k * (R % 2 == 0 ? 2 : 1)];
             x[r] = (DIR < 0) ? cmul(x[r], w) : cmulc(x[r], w);
         }
     }
@@ -77,7 +78,7 @@ template <int N_, int Ra, int Rb> struct MixPlan3 {
                     const Cx<F>* rd = in + (b + hi * D1) * S;
 #pragma unroll
                     for (int r = 0; r < Rb; ++r) x[r] = rd[(r * (Ra * Ra + Ra * D1)) * S];
-                    mix_twiddle<DIR, Rb, F>(x, tw + k * Rb);
+                    mix_twiddle<DIR, Rb, Ra, F>(x, tw, k);
                     Bfly<Rb, DIR, F>::run(x);
                     Cx<F>* wr = out + (hi * (T + D2) + k) * S;
 #pragma unroll
@@ -91,7 +92,7 @@ template <int N_, int Ra, int Rb> struct MixPlan3 {
             const Cx<F>* rd = acc.line(BUF0 ^ 1) + j * S;
 #pragma unroll
             for (int r = 0; r < Ra; ++r) v[r] = rd[(r * (T + D2)) * S];
-            mix_twiddle<DIR, Ra, F>(v, tw + Ra * Rb + j * Ra);
+            mix_twiddle<DIR, Ra, T, F>(v, tw + Ra * Rb, j);
             Bfly<Ra, DIR, F>::run(v);
         }
     }

@@ -55,10 +55,15 @@ template <int... Rs> struct PaddedLine {
 //   static constexpr int STRIDE;            element stride of consecutive line positions
 //   Cx<T>* line(int buf) const;             this thread's line in buffer 0/1
 
-// Twiddles: one table per twiddled pass, laid out [k][R] (k = b mod Ns < Ns, entry r = W^{r k},
-// W = exp(-2 pi i / (Ns R)); entry 0 is 1 and unused) so that a butterfly reads its R-1 factors
-// as R/2 consecutive 16-byte loads from ONE computed address.  Tables of consecutive passes are
+// Twiddles: one table per twiddled pass with entries W^{r k} (k = b mod Ns < Ns, W = exp(-2 pi i / (Ns R)); r = 0 is 1
+// and unused), laid out with k FASTEST: even R as pairs [r/2][k][2] (one 16-byte load fetches W^{2 r2 k}, W^{(2 r2 + 1) k}),
+// odd R as [r][k].  A butterfly still reads its factors from ONE computed address (+ compile-time offsets r2 * Ns), and
+// the lanes of a warp, whose k are consecutive, now read consecutive 16-byte words: a [k][R] layout (80-byte stride
+// between lanes for R = 10) touched five times as many L1 lines per load.  Tables of consecutive passes are
 // concatenated (offset TWOFF).  Host side: spec_twiddle_table().
+__host__ __device__ constexpr int tw_index(int R, int Ns, int r, int k) {
+    return (R % 2 == 0) ? (((r >> 1) * Ns + k) * 2 + (r & 1)) : (r * Ns + k);
+}
 template <int N, int E, int DIR, int Ns, int BUF, int TWOFF, typename T, typename Acc, int... Rs> struct RegPasses;
 
 template <int N, int E, int DIR, int Ns, int BUF, int TWOFF, typename T, typename Acc>
@@ -96,19 +101,19 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
 #pragma unroll
             for (int r = 0; r < R; ++r) x[r] = v[q + r * Q];
             if (Ns > 1) {
-                const Cx<T>* trow = tw + TWOFF + k * R;
                 if constexpr (R % 2 == 0 && sizeof(T) == 4) {
-                    const float4* t4 = reinterpret_cast<const float4*>(trow);
+                    const float4* t4 = reinterpret_cast<const float4*>(tw + TWOFF) + k;
 #pragma unroll
                     for (int r2 = 0; r2 < R / 2; ++r2) {
-                        const float4 w = __ldg(t4 + r2);
+                        const float4 w = __ldg(t4 + r2 * Ns);
                         if (r2 > 0) x[2 * r2] = (DIR < 0) ? cmul(x[2 * r2], cmake<T>(w.x, w.y)) : cmulc(x[2 * r2], cmake<T>(w.x, w.y));
                         x[2 * r2 + 1] = (DIR < 0) ? cmul(x[2 * r2 + 1], cmake<T>(w.z, w.w)) : cmulc(x[2 * r2 + 1], cmake<T>(w.z, w.w));
                     }
                 } else {
+                    const Cx<T>* tp = tw + TWOFF;
 #pragma unroll
                     for (int r = 1; r < R; ++r) {
-                        const Cx<T> w = trow[r];
+                        const Cx<T> w = tp[tw_index(R, Ns, r, 0) + k * (R % 2 == 0 ? 2 : 1)];
                         x[r] = (DIR < 0) ? cmul(x[r], w) : cmulc(x[r], w);
                     }
                 }

@@ -357,10 +357,12 @@ template <typename F> static std::vector<Cx<F>> spec_twiddle_table_t(const std::
     for (size_t p = 0; p < radices.size(); ++p) {
         const int R = radices[p];
         if (Ns > 1) {
+            const size_t base = t.size();
+            t.resize(base + (size_t)Ns * R);
             for (long k = 0; k < Ns; ++k)
                 for (int r = 0; r < R; ++r) {
                     const double ang = -2.0 * M_PI * (double)((r * k) % (Ns * R)) / (double)(Ns * R);
-                    t.push_back(cmake<F>((F)cos(ang), (F)sin(ang)));
+                    t[base + tw_index(R, (int)Ns, r, (int)k)] = cmake<F>((F)cos(ang), (F)sin(ang));
                 }
         }
         Ns *= R;
