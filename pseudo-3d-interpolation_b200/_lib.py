@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libp3d_b200.so")
+LIB_PATH = os.environ.get("P3D_LIB") or os.path.join(_HERE, "csrc", "libp3d_b200.so")   # P3D_LIB: A/B builds (tools)
 
 OK = 0
 ERR_BAD_ARG, ERR_NOT_IMPLEMENTED, ERR_CUDA, ERR_OOM, ERR_NUMERIC = -1, -2, -3, -4, -5
