@@ -412,6 +412,35 @@ def test_config3_plans_match_generic_and_oracle(shape, op, model, alpha, version
         assert np.array_equal(y[:, obs], x[:, obs])
 
 
+MORE_SIZES = [128, 512, 1024, 2048, 400, 500, 800, 1600, 300, 600, 700, 900, 1100, 1300, 1200, 2400]
+
+
+@pytest.mark.parametrize("n", MORE_SIZES)
+def test_more_register_plans_match_oracle(n, p3d):
+    """every further length with a register plan (p3d_pocs_spec_more.cu, p3d_pocs_spec_mix.cu), as the iline axis and
+    as the xline axis (the other axis runs the generic kernels), against the float64 oracle."""
+    for shape in ((n, 24), (20, n)):
+        x, mask = make_input(dict(seed=n, shape=shape, keep=0.3, nwaves=4))
+        x = np.stack([x, 0.5 * np.conj(x)]).astype(np.complex64)
+        params = dict(niter=5, thresh_op="soft", thresh_model="linear", eps=0.0, alpha=0.8, p_max=0.99, p_min=1e-3)
+        plan = p3d.PocsPlan(*shape)
+        d = plan.describe()
+        key = "cols_iter=" if shape[0] == n else "rows_iter="
+        assert f"<{n}," in d.split(key)[1].split(";")[0], d
+        y, info = plan.run(x, mask, **params)
+        for i in range(2):
+            ref = orc.pocs_slice(x[i].astype(np.complex128), mask, **params)
+            assert rel_l2(y[i], ref) <= RTOL, (shape, i, rel_l2(y[i], ref))
+    # square slice of this size: both axes on register plans, hard threshold, observed traces exact
+    if n <= 1024:
+        x, mask = make_input(dict(seed=n + 1, shape=(n, n), keep=0.25, nwaves=5))
+        params = dict(niter=4, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-2)
+        y, _ = p3d.PocsPlan(n, n).run(x.astype(np.complex64), mask, **params)
+        ref = orc.pocs_slice(x.astype(np.complex128), mask, **params)
+        assert rel_l2(y[0], ref) <= 2e-3
+        assert np.array_equal(y[0][mask == 1], x.astype(np.complex64)[mask == 1])
+
+
 def test_per_cube_masks(p3d):
     """config-5 style batch: independent cubes, each with its own mask (slices_per_mask)."""
     rng = np.random.default_rng(3)
