@@ -239,6 +239,7 @@ template <int DIR, typename T> struct Bfly<9, DIR, T>  { __device__ __forceinlin
 template <int DIR, typename T> struct Bfly<10, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<2, 5, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<12, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<4, 3, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<16, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<4, 4, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<30, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<5, 6, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<20, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<4, 5, DIR, T>::run(v); } };
 
 }  // namespace p3d

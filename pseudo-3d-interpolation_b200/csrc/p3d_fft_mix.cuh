@@ -13,7 +13,7 @@
 // Exchange layout: as in p3d_fft_reg.cuh, position pos written by the pass with Stockham block
 // B = Ns*R is stored at pos + (pos / B) * DELTA (bank spreading); all addresses split into a
 // per-thread base plus compile-time offsets.
-// Twiddles: the tables of spec_twiddle_table({Ra, Rb, Ra}) (pass 2 at offset 0, pass 3 at Ra*Rb; layout: tw_index).
+// Twiddles: the tables of spec_twiddle_table({Ra, Rb, Ra}) (pass 2 at offset 0, pass 3 at Ra*Rb rounded up to even; layout: tw_index).
 #pragma once
 #include "p3d_fft_reg.cuh"
 
@@ -92,7 +92,7 @@ template <int N_, int Ra, int Rb> struct MixPlan3 {
             const Cx<F>* rd = acc.line(BUF0 ^ 1) + j * S;
 #pragma unroll
             for (int r = 0; r < Ra; ++r) v[r] = rd[(r * (T + D2)) * S];
-            mix_twiddle<DIR, Ra, T, F>(v, tw + Ra * Rb, j);
+            mix_twiddle<DIR, Ra, T, F>(v, tw + ((Ra * Rb + 1) & ~1), j);
             Bfly<Ra, DIR, F>::run(v);
         }
     }

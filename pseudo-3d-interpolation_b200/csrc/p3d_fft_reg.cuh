@@ -60,7 +60,7 @@ template <int... Rs> struct PaddedLine {
 // odd R as [r][k].  A butterfly still reads its factors from ONE computed address (+ compile-time offsets r2 * Ns), and
 // the lanes of a warp, whose k are consecutive, now read consecutive 16-byte words: a [k][R] layout (80-byte stride
 // between lanes for R = 10) touched five times as many L1 lines per load.  Tables of consecutive passes are
-// concatenated (offset TWOFF).  Host side: spec_twiddle_table().
+// concatenated (offset TWOFF, each table starting at an even element = 16-byte aligned).  Host side: spec_twiddle_table().
 __host__ __device__ constexpr int tw_index(int R, int Ns, int r, int k) {
     return (R % 2 == 0) ? (((r >> 1) * Ns + k) * 2 + (r & 1)) : (r * Ns + k);
 }
@@ -152,7 +152,7 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = rd[(e * TT + DELTA * (e / (B / TT))) * S];
             }
-            RegPasses<N, E, DIR, Ns * R, BUF ^ 1, TWOFF + (Ns > 1 ? Ns * R : 0), T, Acc, Rest...>::run(v, acc, j, tw);
+            RegPasses<N, E, DIR, Ns * R, BUF ^ 1, TWOFF + (Ns > 1 ? ((Ns * R + 1) & ~1) : 0), T, Acc, Rest...>::run(v, acc, j, tw);
         }
     }
 };

@@ -169,6 +169,7 @@ template <typename MP, int P> static std::vector<Cx<float>> rader_tables() {
     constexpr int M = P - 1;
     int rad[3]; MP::radices(rad);
     std::vector<Cx<float>> t = spec_twiddle_table(std::vector<int>(rad, rad + 3));
+    static_assert(MP::T % 2 == 0, "Rader table offsets assume an even pass-2 table");
     t.resize((size_t)MP::T + M);                                    // exact size of the twiddle section
     const int g = primitive_root(P);
     const long ginv = powmod(g, P - 2, P);

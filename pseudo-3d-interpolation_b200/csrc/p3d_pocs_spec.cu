@@ -23,6 +23,7 @@ template <typename F> static std::vector<Cx<F>> spec_twiddle_table_t(const std::
                     const double ang = -2.0 * M_PI * (double)((r * k) % (Ns * R)) / (double)(Ns * R);
                     t[base + tw_index(R, (int)Ns, r, (int)k)] = cmake<F>((F)cos(ang), (F)sin(ang));
                 }
+            if (t.size() & 1) t.push_back(cmake<F>(F(0), F(0)));      // every table starts 16-byte aligned
         }
         Ns *= R;
     }

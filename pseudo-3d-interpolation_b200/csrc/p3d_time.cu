@@ -177,7 +177,7 @@ k_time_fwd_spec(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
     for (int e = 0; e < E; ++e) {
         const int k = j + e * T;
         if (k < G.nf) {
-            const int km = (N - k) & (N - 1);
+            const int km = (k == 0) ? 0 : N - k;
             const Cx<float> z1 = v[e], z2 = buf[km * C];
             const Cx<float> xa = cmake<float>(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
             const Cx<float> xb = cmake<float>(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
@@ -212,7 +212,7 @@ k_time_inv_spec(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
         const bool have = G.compute_real ? (k <= half) : true;
         if (ok && have) {
             long long row = k;
-            if (!G.compute_real && G.ascending) row = (k + half) & (N - 1);
+            if (!G.compute_real && G.ascending) row = (k + half) % N;
             const float4 p = *reinterpret_cast<const float4*>(F + row * G.ntr + tr);
             const Cx<float> ph = phase[k];
             ga[e] = cmul(cmake<float>(p.x, p.y), ph);
@@ -226,7 +226,7 @@ k_time_inv_spec(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int k = j + e * T;
-        const int km = (N - k) & (N - 1);
+        const int km = (k == 0) ? 0 : N - k;
         const Cx<float> a2 = bufA[km * C], b2 = bufB[km * C];
         Cx<float> ha, hb;
         if (G.compute_real) {
@@ -252,6 +252,13 @@ typedef LinePlan<512, 16, 16, 16, 2> TP512;
 typedef LinePlan<1024, 16, 16, 16, 4> TP1024;
 typedef LinePlan<2048, 16, 16, 16, 8> TP2048;
 typedef LinePlan<4096, 16, 16, 16, 16> TP4096;
+// 10-smooth record lengths (1 / 2 / 4 ms sampling of 1 - 5 s records)
+typedef LinePlan<1000, 10, 10, 10, 10> TP1000;
+typedef LinePlan<2000, 20, 20, 10, 10> TP2000;
+typedef LinePlan<2500, 10, 5, 5, 10, 10> TP2500;
+typedef LinePlan<3000, 30, 10, 10, 30> TP3000;
+typedef LinePlan<4000, 20, 20, 20, 10> TP4000;
+typedef LinePlan<5000, 10, 10, 10, 10, 5> TP5000;
 
 // ------------------------------------------------------------------------------------------------
 // Transposing pipeline (the default for the record lengths above).  The time axis is the slowest
@@ -317,7 +324,7 @@ k_time_fwd_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
     for (int e = 0; e < E; ++e) {
         const int k = j + e * T;
         if (k < G.nf) {
-            const Cx<float> z1 = v[e], z2 = buf[(N - k) & (N - 1)];
+            const Cx<float> z1 = v[e], z2 = buf[(k == 0) ? 0 : N - k];
             const Cx<float> xa = cmake<float>(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
             const Cx<float> xb = cmake<float>(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
             const Cx<float> ph = phase[k];
@@ -352,7 +359,7 @@ k_time_inv_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
         const bool have = G.compute_real ? (k <= half) : true;
         if (have) {
             int row = k;
-            if (!G.compute_real && G.ascending) row = (k + half) & (N - 1);
+            if (!G.compute_real && G.ascending) row = (k + half) % N;
             const Cx<float> ph = phase[k];
             if (oka) ga[e] = cmul(ia[row], ph);
             if (okb) gb[e] = cmul(ib[row], ph);
@@ -365,7 +372,7 @@ k_time_inv_rows(const __grid_constant__ TimeGeom G, const Cx<float>* __restrict_
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int k = j + e * T;
-        const int km = (N - k) & (N - 1);
+        const int km = (k == 0) ? 0 : N - k;
         const Cx<float> a2 = bufA[km], b2 = bufB[km];
         Cx<float> ha, hb;
         if (G.compute_real) {
@@ -567,6 +574,12 @@ bool try_time_spec(const TimeGeom& G, const void* din, void* dout, const Cx<floa
             case 1024: return launch_time_pipeline<TP1024, 4>(G, din, dout, d_ph, inverse, smem_optin);
             case 2048: return launch_time_pipeline<TP2048, 2>(G, din, dout, d_ph, inverse, smem_optin);
             case 4096: return launch_time_pipeline<TP4096, 1>(G, din, dout, d_ph, inverse, smem_optin);
+            case 1000: return launch_time_pipeline<TP1000, 4>(G, din, dout, d_ph, inverse, smem_optin);
+            case 2000: return launch_time_pipeline<TP2000, 2>(G, din, dout, d_ph, inverse, smem_optin);
+            case 2500: return launch_time_pipeline<TP2500, 2>(G, din, dout, d_ph, inverse, smem_optin);
+            case 3000: return launch_time_pipeline<TP3000, 1>(G, din, dout, d_ph, inverse, smem_optin);
+            case 4000: return launch_time_pipeline<TP4000, 1>(G, din, dout, d_ph, inverse, smem_optin);
+            case 5000: return launch_time_pipeline<TP5000, 1>(G, din, dout, d_ph, inverse, smem_optin);
             default: return false;
         }
     }
@@ -646,7 +659,10 @@ int time_impl(int device, const void* x, int x_mem, void* out, int out_mem, int6
     // the generic direct kernels need an axis plan; the register-resident pipeline (record lengths
     // 512 .. 4096) does not, so it is only built when that path declines
     static const bool no_spec = getenv("P3D_TIME_GENERIC") != nullptr;
-    const bool spec_len = !no_spec && (nfft == 512 || nfft == 1024 || nfft == 2048 || nfft == 4096);
+    static const bool direct_only = getenv("P3D_TIME_DIRECT") != nullptr;       // the direct register kernels exist for powers of two
+    const bool pow2_len = nfft == 512 || nfft == 1024 || nfft == 2048 || nfft == 4096;
+    const bool smooth_len = nfft == 1000 || nfft == 2000 || nfft == 2500 || nfft == 3000 || nfft == 4000 || nfft == 5000;
+    const bool spec_len = !no_spec && (pow2_len || (smooth_len && !direct_only));
     AxisPlan ax;
     struct Cleanup { AxisPlan* a; void* p[3]; ~Cleanup() { a->release(); for (void* q : p) if (q) cudaFree(q); } } cl{&ax, {nullptr, nullptr, nullptr}};
     int C = 1; size_t smem = 0;
@@ -731,6 +747,12 @@ int envelope_impl(int device, const float* x, int x_mem, float* out, int out_mem
             case 1024: done = launch_env_pipeline<TP1024, 4>(G, din, dout, (size_t)optin); break;
             case 2048: done = launch_env_pipeline<TP2048, 2>(G, din, dout, (size_t)optin); break;
             case 4096: done = launch_env_pipeline<TP4096, 1>(G, din, dout, (size_t)optin); break;
+            case 1000: done = launch_env_pipeline<TP1000, 4>(G, din, dout, (size_t)optin); break;
+            case 2000: done = launch_env_pipeline<TP2000, 2>(G, din, dout, (size_t)optin); break;
+            case 2500: done = launch_env_pipeline<TP2500, 2>(G, din, dout, (size_t)optin); break;
+            case 3000: done = launch_env_pipeline<TP3000, 1>(G, din, dout, (size_t)optin); break;
+            case 4000: done = launch_env_pipeline<TP4000, 1>(G, din, dout, (size_t)optin); break;
+            case 5000: done = launch_env_pipeline<TP5000, 1>(G, din, dout, (size_t)optin); break;
             default: break;
         }
     }

@@ -39,7 +39,8 @@ def test_gpu_envelope_matches_reference_golden(case, gold):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nt,ntr", [(512, 1001), (1024, 130), (2048, 64), (4096, 7), (300, 33), (1201, 5), (1, 4), (2, 3)])
+@pytest.mark.parametrize("nt,ntr", [(512, 1001), (1024, 130), (2048, 64), (4096, 7), (300, 33), (1201, 5), (1, 4), (2, 3),
+                                    (1000, 37), (2000, 9), (2500, 5), (3000, 11), (4000, 3), (5000, 4)])
 def test_gpu_envelope_lengths_and_axes(nt, ntr):
     """register-resident pipeline (512 ... 4096, odd trace counts), generic direct kernel (any length, Bluestein),
     degenerate lengths; other axes go through a time-major view."""

@@ -531,7 +531,10 @@ def test_time_axis_window(p3d):
 
 @pytest.mark.parametrize("nt,shape,real,up", [(512, (9, 7), True, 1), (512, (9, 7), False, 1), (256, (5, 11), True, 2),
                                               (1024, (6, 5), True, 1), (2048, (3, 5), False, 1), (4096, (2, 3), True, 1),
-                                              (300, (4, 5), True, 1), (1201, (2, 2), False, 1)])
+                                              (300, (4, 5), True, 1), (1201, (2, 2), False, 1),
+                                              (1000, (7, 9), True, 1), (1000, (3, 5), False, 1), (2000, (5, 3), True, 1), (2500, (3, 3), True, 1),
+                                              (3000, (5, 7), True, 1), (3000, (2, 3), False, 1), (4000, (2, 5), True, 1), (5000, (3, 1), True, 1),
+                                              (1500, (3, 3), True, 2)])
 def test_time_axis_register_pipeline_sizes(nt, shape, real, up, p3d):
     """record lengths served by the transposing register-resident pipeline (512..4096, here with
     odd trace counts and zero padding) and generic / Bluestein lengths, vs the numpy oracle."""
