@@ -21,6 +21,7 @@
 #include <cmath>
 #include <complex>
 #include <cstring>
+#include <cstdint>
 
 namespace p3d {
 
@@ -30,7 +31,8 @@ __device__ __forceinline__ Cx<float> ldg_cx(const Cx<float>* p) {
 }
 
 // MODE 0: statistics of X0 (+ optional store), MODE 1: iterate (threshold / filter)
-template <typename MP, int P, int C, int MINB, int MODE>
+// BULK: tile load with cp.async.cg into exchange buffer 1 (see k_cols_spec), the row permutation applied to the SOURCE row
+template <typename MP, int P, int C, int MINB, int MODE, bool BULK>
 __global__ void __launch_bounds__(MP::T* C, MINB)
 k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tab, const __grid_constant__ BandArgs<float> A, const int op) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -53,13 +55,34 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
 #pragma unroll
     for (int e = 0; e < E; ++e) row[e] = __ldg(perm + j + e * T);
     Cx<float> v[E];
+    constexpr int CHUNKS = (C * (int)sizeof(Cx<float>)) / 16;
+    const bool bulk = BULK && (CHUNKS >= 1) && (blockIdx.x * C + C <= G.n2) && (((long long)G.n2 * sizeof(Cx<float>)) % 16 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(A.W) % 16) == 0);
+    if (bulk) {
+        const char* src0 = reinterpret_cast<const char*>(A.W + (long long)s * P * G.n2 + blockIdx.x * C);
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(reinterpret_cast<Cx<float>*>(smem_raw) + (size_t)MP::LINE * C);
+        for (int q = tid; q < M * CHUNKS; q += T * C) {
+            const int m = q / CHUNKS, part = q - m * CHUNKS;
+            const char* src = src0 + (long long)__ldg(perm + m) * G.n2 * sizeof(Cx<float>) + part * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (unsigned)(m * C * sizeof(Cx<float>) + part * 16)), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;");
+    } else {
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)row[e] * G.n2] : cmake<float>(0.f, 0.f);
+        for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)row[e] * G.n2] : cmake<float>(0.f, 0.f);
+    }
     Cx<float> dc = (ok && j == 0) ? Ws[0] : cmake<float>(0.f, 0.f);
     Cx<float> tau = cmake<float>(0.f, 0.f);
     if (MODE == 1) {
         tau = A.tau[(long long)s * A.niter + A.k];
-        if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) return;
+        if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
+    }
+    if (bulk) {
+        asm volatile("cp.async.wait_all;");
+        __syncthreads();
+        const Cx<float>* land = acc.line(1);
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = land[(j + e * T) * C];
     }
 
     // ---- forward DFT of length P
@@ -202,16 +225,16 @@ template <typename MP, int P> static std::vector<Cx<float>> rader_tables() {
     return t;
 }
 
-template <typename MP, int P, int C, int MINB, int MODE>
+template <typename MP, int P, int C, int MINB, int MODE, bool BULK = false>
 static void launch_rader(const PocsGeom& G, const Cx<float>* tab, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
     constexpr size_t smem = (size_t)2 * MP::LINE * C * sizeof(Cx<float>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_cols_rader<MP, P, C, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cols_rader<MP, P, C, MINB, MODE, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n2 + C - 1) / C, ns);
-    k_cols_rader<MP, P, C, MINB, MODE><<<grid, MP::T * C, smem, st>>>(G, tab, A, op);
+    k_cols_rader<MP, P, C, MINB, MODE, BULK><<<grid, MP::T * C, smem, st>>>(G, tab, A, op);
 }
 template <typename MP, int P, int C, int MINB>
 static void launch_rader_stats(const PocsGeom& G, const Cx<float>* tab, const BandArgs<float>& A, int ns, cudaStream_t st) {
@@ -223,30 +246,26 @@ typedef MixPlan3<1200, 20, 3> MP1200E20;
 
 void rader_register_cols(SpecKernels& k, int n_iline, int variant) {
     if (n_iline != 1201) return;
+    k.cols_radices = {20, 3, 20};
+    k.cols_table = rader_tables<MP1200E20, 1201>;
     if (variant == 1) {
-        k.cols_iter = launch_rader<MP1200, 1201, 2, 4, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 2, 4>;
-        k.cols_name = "rader<1201,10x12x10,C2,4cta>";
+        k.cols_iter = launch_rader<MP1200E20, 1201, 4, 2, 1, true>; k.cols_stats = launch_rader_stats<MP1200E20, 1201, 4, 2>;
+        k.cols_name = "rader<1201,20x3x20,C4,2cta,cp.async>";
     } else if (variant == 2) {
-        k.cols_iter = launch_rader<MP1200, 1201, 4, 1, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 4, 1>;
-        k.cols_name = "rader<1201,10x12x10,C4,1cta>";
-    } else if (variant == 0) {
+        k.cols_iter = launch_rader<MP1200E20, 1201, 2, 4, 1, true>; k.cols_stats = launch_rader_stats<MP1200E20, 1201, 4, 2>;
+        k.cols_name = "rader<1201,20x3x20,C2,4cta,cp.async>";
+    } else if (variant == 3) {
+        k.cols_iter = launch_rader<MP1200E20, 1201, 2, 5, 1, true>; k.cols_stats = launch_rader_stats<MP1200E20, 1201, 4, 2>;
+        k.cols_name = "rader<1201,20x3x20,C2,5cta,cp.async>";
+    } else if (variant == 4) {
+        k.cols_iter = launch_rader<MP1200, 1201, 4, 2, 1, true>; k.cols_stats = launch_rader_stats<MP1200, 1201, 4, 2>;
+        k.cols_name = "rader<1201,10x12x10,C4,2cta,cp.async>";
+        k.cols_radices = {10, 12, 10};
+        k.cols_table = rader_tables<MP1200, 1201>;
+    } else {       // the Rader kernel is bound by its four transforms, not by the tile load: cp.async changes nothing (1500 vs 1485 us)
         k.cols_iter = launch_rader<MP1200E20, 1201, 4, 2, 1>; k.cols_stats = launch_rader_stats<MP1200E20, 1201, 4, 2>;
         k.cols_name = "rader<1201,20x3x20,C4,2cta>";
-        k.cols_radices = {20, 3, 20};
-        k.cols_table = rader_tables<MP1200E20, 1201>;
-        return;
-    } else if (variant == 4) {
-        k.cols_iter = launch_rader<MP1200E20, 1201, 8, 1, 1>; k.cols_stats = launch_rader_stats<MP1200E20, 1201, 8, 1>;
-        k.cols_name = "rader<1201,20x3x20,C8,1cta>";
-        k.cols_radices = {20, 3, 20};
-        k.cols_table = rader_tables<MP1200E20, 1201>;
-        return;
-    } else {   // variant 3
-        k.cols_iter = launch_rader<MP1200, 1201, 4, 2, 1>; k.cols_stats = launch_rader_stats<MP1200, 1201, 4, 2>;
-        k.cols_name = "rader<1201,10x12x10,C4,2cta>";
     }
-    k.cols_radices = {10, 12, 10};
-    k.cols_table = rader_tables<MP1200, 1201>;
 }
 
 }  // namespace p3d

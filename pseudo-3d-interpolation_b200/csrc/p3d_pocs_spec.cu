@@ -45,24 +45,31 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
     SpecKernels k;
     switch (n_iline) {      // column transforms have the length of the iline axis
         case 1000:
-            if (variant == 1) P3D_COLS(LP1000, 8, 1, "spec<1000,E10,10x10x10,C8,1cta>");
-            else if (variant == 6) P3D_COLS(LP1000, 4, 3, "spec<1000,E10,10x10x10,C4,3cta>");
-            else if (variant == 7) P3D_COLS(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta>");
-            else if (variant == 8) P3D_COLS(LP1000E20, 8, 1, "spec<1000,E20,10x10x10,C8,1cta>");
-            else if (variant == 2) { k.cols_iter = launch_cols<LP1000, 4, 2, true>; k.cols_name = "spec<1000,E10,10x10x10,C4,2cta,l2prefetch>"; k.cols_radices = radices_of<LP1000>(); }
-            else if (variant == 4) P3D_COLS(LP1000, 2, 4, "spec<1000,E10,10x10x10,C2,4cta>");
-            else if (variant == 12) P3D_COLS(LP1000E20, 4, 3, "spec<1000,E20,10x10x10,C4,3cta>");
-            else              P3D_COLS(LP1000E20, 4, 2, "spec<1000,E20,10x10x10,C4,2cta>");
+            if (variant == 1) P3D_COLS(LP1000E20, 4, 2, "spec<1000,E20,10x10x10,C4,2cta>");
+            else if (variant == 2) P3D_COLS_BULK(LP1000E20, 4, 2, "spec<1000,E20,10x10x10,C4,2cta,cp.async>");
+            else if (variant == 3) P3D_COLS_BULK(LP1000, 4, 3, "spec<1000,E10,10x10x10,C4,3cta,cp.async>");
+            else if (variant == 4) P3D_COLS_BULK(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta,cp.async>");
+            else if (variant == 5) P3D_COLS_BULK(LP1000E20, 8, 1, "spec<1000,E20,10x10x10,C8,1cta,cp.async>");
+            else if (variant == 6) P3D_COLS_BULK(LP1000E20, 2, 4, "spec<1000,E20,10x10x10,C2,4cta,cp.async>");
+            else              P3D_COLS_BULK(LP1000E20, 4, 3, "spec<1000,E20,10x10x10,C4,3cta,cp.async>");
             break;
         case 2000:
-            if (variant == 4) P3D_COLS(LP2000, 2, 2, "spec<2000,E10,10x10x10x2,C2,2cta>");
-            else if (variant == 5) P3D_COLS(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4>");
-            else if (variant == 6) P3D_COLS(LP2000E20, 4, 2, "spec<2000,E20,20x10x10,C4,2cta>");
-            else if (variant == 7) P3D_COLS(LP2000E20, 2, 2, "spec<2000,E20,20x10x10,C2,2cta>");
-            else              P3D_COLS(LP2000E20, 4, 1, "spec<2000,E20,20x10x10,C4,1cta>");
+            if (variant == 1) P3D_COLS_BULK(LP2000E20, 4, 1, "spec<2000,E20,20x10x10,C4,1cta,cp.async>");
+            else if (variant == 2) P3D_COLS_BULK(LP2000, 4, 1, "spec<2000,E10,10x10x10x2,C4,1cta,cp.async>");
+            else if (variant == 3) P3D_COLS(LP2000E20, 4, 1, "spec<2000,E20,20x10x10,C4,1cta>");
+            else              P3D_COLS_BULK(LP2000E20, 2, 3, "spec<2000,E20,20x10x10,C2,3cta,cp.async>");
             break;
-        case 256:  P3D_COLS(LP256, 16, 3, "spec<256,E16,16x16,C16>"); break;
-        case 200:  P3D_COLS(LP200, 16, 4, "spec<200,E20,10x20,C16>"); break;
+        case 256:
+            if (variant == 1) P3D_COLS(LP256, 16, 3, "spec<256,E16,16x16,C16>");
+            else if (variant == 2) P3D_COLS_BULK(LP256, 16, 4, "spec<256,E16,16x16,C16,4cta,cp.async>");
+            else if (variant == 3) P3D_COLS_BULK(LP256, 16, 3, "spec<256,E16,16x16,C16,cp.async>");
+            else              P3D_COLS_BULK(LP256, 8, 6, "spec<256,E16,16x16,C8,6cta,cp.async>");
+            break;
+        case 200:
+            if (variant == 1) P3D_COLS(LP200, 16, 4, "spec<200,E20,10x20,C16>");
+            else if (variant == 2) P3D_COLS_BULK(LP200, 16, 5, "spec<200,E20,10x20,C16,5cta,cp.async>");
+            else              P3D_COLS_BULK(LP200, 16, 4, "spec<200,E20,10x20,C16,cp.async>");
+            break;
         default:
             rader_register_cols(k, n_iline, variant);
             if (!k.cols_iter && !more_register_cols(k, n_iline)) mix_register_cols(k, n_iline);

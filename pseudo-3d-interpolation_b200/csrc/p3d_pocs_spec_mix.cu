@@ -15,14 +15,14 @@ typedef MixPlan3<2400, 20, 6> MP2400;
 
 bool mix_register_cols(SpecKernels& k, int n_iline) {
     switch (n_iline) {
-        case 300:  P3D_COLS(MP300, 8, 4, "mix<300,10x3x10,C8>"); return true;
-        case 600:  P3D_COLS(MP600, 4, 4, "mix<600,10x6x10,C4>"); return true;
-        case 700:  P3D_COLS(MP700, 4, 3, "mix<700,10x7x10,C4>"); return true;
-        case 900:  P3D_COLS(MP900, 4, 2, "mix<900,10x9x10,C4>"); return true;
-        case 1100: P3D_COLS(MP1100, 4, 2, "mix<1100,10x11x10,C4>"); return true;
-        case 1300: P3D_COLS(MP1300, 4, 2, "mix<1300,10x13x10,C4>"); return true;
-        case 1200: P3D_COLS(MP1200, 4, 2, "mix<1200,20x3x20,C4>"); return true;
-        case 2400: P3D_COLS(MP2400, 4, 1, "mix<2400,20x6x20,C4>"); return true;
+        case 300:  P3D_COLS_BULK(MP300, 8, 5, "mix<300,10x3x10,C8,cp.async>"); return true;
+        case 600:  P3D_COLS_BULK(MP600, 4, 5, "mix<600,10x6x10,C4,cp.async>"); return true;
+        case 700:  P3D_COLS_BULK(MP700, 4, 4, "mix<700,10x7x10,C4,cp.async>"); return true;
+        case 900:  P3D_COLS_BULK(MP900, 4, 3, "mix<900,10x9x10,C4,cp.async>"); return true;
+        case 1100: P3D_COLS_BULK(MP1100, 4, 2, "mix<1100,10x11x10,C4,cp.async>"); return true;
+        case 1300: P3D_COLS_BULK(MP1300, 4, 2, "mix<1300,10x13x10,C4,cp.async>"); return true;
+        case 1200: P3D_COLS_BULK(MP1200, 4, 2, "mix<1200,20x3x20,C4,cp.async>"); return true;
+        case 2400: P3D_COLS_BULK(MP2400, 2, 2, "mix<2400,20x6x20,C2,cp.async>"); return true;
         default: return false;
     }
 }

@@ -17,14 +17,14 @@ typedef LinePlan<1600, 20, 20, 20, 4> LP1600;
 
 bool more_register_cols(SpecKernels& k, int n_iline) {
     switch (n_iline) {
-        case 128:  P3D_COLS(LP128, 16, 4, "spec<128,E16,16x8,C16>"); return true;
-        case 512:  P3D_COLS(LP512, 8, 3, "spec<512,E16,16x16x2,C8>"); return true;
-        case 1024: P3D_COLS(LP1024, 4, 3, "spec<1024,E16,16x16x4,C4>"); return true;
-        case 2048: P3D_COLS(LP2048, 4, 1, "spec<2048,E16,16x16x8,C4>"); return true;
-        case 400:  P3D_COLS(LP400, 8, 3, "spec<400,E20,20x20,C8>"); return true;
-        case 500:  P3D_COLS(LP500, 4, 4, "spec<500,E10,10x10x5,C4>"); return true;
-        case 800:  P3D_COLS(LP800, 4, 3, "spec<800,E20,20x20x2,C4>"); return true;
-        case 1600: P3D_COLS(LP1600, 4, 1, "spec<1600,E20,20x20x4,C4>"); return true;
+        case 128:  P3D_COLS_BULK(LP128, 16, 5, "spec<128,E16,16x8,C16,cp.async>"); return true;
+        case 512:  P3D_COLS_BULK(LP512, 8, 3, "spec<512,E16,16x16x2,C8,cp.async>"); return true;
+        case 1024: P3D_COLS_BULK(LP1024, 4, 3, "spec<1024,E16,16x16x4,C4,cp.async>"); return true;
+        case 2048: P3D_COLS_BULK(LP2048, 2, 3, "spec<2048,E16,16x16x8,C2,cp.async>"); return true;
+        case 400:  P3D_COLS_BULK(LP400, 8, 4, "spec<400,E20,20x20,C8,cp.async>"); return true;
+        case 500:  P3D_COLS_BULK(LP500, 4, 5, "spec<500,E10,10x10x5,C4,cp.async>"); return true;
+        case 800:  P3D_COLS_BULK(LP800, 4, 4, "spec<800,E20,20x20x2,C4,cp.async>"); return true;
+        case 1600: P3D_COLS_BULK(LP1600, 4, 2, "spec<1600,E20,20x20x4,C4,cp.async>"); return true;
         default: return false;
     }
 }
