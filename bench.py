@@ -368,6 +368,11 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
+                # DRAM bytes actually moved (ncu) over the same launch time: the fused kernels move less than the
+                # four-pass model counts (the row kernel writes the result only in the last iteration), so `frac` may
+                # exceed 1 while DRAM itself is not saturated
+                "dram_achieved_GBps": (traffic / (avg_ms * 1e-3) / 1e9) if traffic else None,
+                "note": "achieved = SURVEY 8(d) model bytes (73 B/element/iteration, split 32 cols + 41 rows) / measured launch time",
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                 "whole_iteration": {"alg_bytes_per_slice_iteration": B_ALG_PER_ELEM * n1 * n2,
                                     "achieved_GBps": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9,

@@ -131,7 +131,8 @@ SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant) {
         case 1000:
             if (variant == 1) P3D_COLS64(LP1000, 4, 1, "spec64<1000,E10,10x10x10,C4,1cta>");
             else if (variant == 2) P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta>");
-            else              P3D_COLS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,C2,2cta>");
+            else if (variant == 3) P3D_COLS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,C2,2cta>");
+            else { P3D_COLS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,C2,2cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 2, 2, true, double>; }
             break;
         case 2000:
             if (variant == 1) P3D_COLS64(LP2000, 1, 3, "spec64<2000,E10,10x10x10x2,C1,3cta>");
