@@ -629,5 +629,11 @@ def test_run_to_run_determinism_all_kernel_families():
     filter, envelope, time axis) repeated on the same input: bit-identical results (tools/sanitize_cases.py)."""
     import os
     import runpy
+    import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    runpy.run_path(os.path.join(root, "tools", "sanitize_cases.py"), run_name="__main__")
+    argv, sys.argv = sys.argv, ["sanitize_cases.py", "all"]
+    try:
+        glb = runpy.run_path(os.path.join(root, "tools", "sanitize_cases.py"), run_name="__main__")
+    finally:
+        sys.argv = argv
+    assert glb["only"] == "all" and glb["CASES_RUN"] >= 16

@@ -17,7 +17,12 @@ from pseudo_3d_interpolation_b200 import timeaxis, cube_postprocessing_3D as pos
 from oracle.golden_cases import make_input                                      # noqa: E402
 
 
+CASES_RUN = 0
+
+
 def run(shape, precision=32, **kw):
+    global CASES_RUN
+    CASES_RUN += 1
     x, mask = make_input(dict(seed=3, shape=shape, keep=0.3))
     x = np.stack([x, 0.5 * x]).astype(np.complex64)
     params = dict(niter=4, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-3)
@@ -54,4 +59,5 @@ if only in ("all", "aux"):
         twt = 725.0 + 0.05 * np.arange(nt)
         F, _ = timeaxis.time_fft(x.reshape(nt, ntr, 1), twt, compute_real=True)
         timeaxis.time_ifft(F, 0.05, 725.0, compute_real=True)
+    CASES_RUN += 1
     print("ok aux", flush=True)
