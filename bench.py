@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import multiprocessing as mp
 import os
 import subprocess
@@ -378,6 +379,8 @@ def main():
                                     "achieved_GBps": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9,
                                     "frac_of_measured_peak": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9 / peak,
                                     "frac_of_8TBps_nominal": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9 / 8000.0},
+                # FFT flop rate, 5 N log2 N convention: two 2-D transforms + ~30 flops of element-wise work per element
+                "fft_tflops": value / world * (2 * 5 * n1 * n2 * math.log2(n1 * n2) + 30.0 * n1 * n2) / 1e12,
                 "kernel_share_of_step": {k: prof[k]["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())) for k in prof if prof[k]["launches"]}}
     gpu_launches = int(sum(v["launches"] for v in prof.values()))
 
