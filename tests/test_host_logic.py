@@ -122,3 +122,47 @@ def test_freq_filter_window_matches_oracle():
     for ftype, freqs in (("lowpass", [3.0, 5.0]), ("highpass", [0.5, 1.5]), ("bandpass", [0.5, 1.5, 4.0, 6.0])):
         np.testing.assert_array_equal(timeaxis.freq_filter_window(list(freqs), f, ftype), tor.freq_filter_window(list(freqs), f, ftype))
         np.testing.assert_array_equal(timeaxis.freq_filter_keep(f, freqs, ftype), tor.freq_filter_keep(f, freqs, ftype))
+
+
+def test_numa_binding_helpers(tmp_path, monkeypatch):
+    """cpulist parsing and the sysfs walk of bind_to_gpu_numa_node on a fake /sys tree (no GPU, no NVML needed)."""
+    from pseudo_3d_interpolation_b200 import distributed as pd
+    assert pd._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert pd._parse_cpulist("") == []
+    # unknown GPU -> not bound, never raises
+    assert "not bound" in pd.bind_to_gpu_numa_node(0, sysfs=str(tmp_path))
+    # fake topology: GPU on node 1 whose cpus are the ones this process may use
+    monkeypatch.setattr(pd, "gpu_numa_node", lambda dev, sysfs="/sys": 1)
+    node = tmp_path / "devices" / "system" / "node" / "node1"
+    node.mkdir(parents=True)
+    allowed = sorted(os.sched_getaffinity(0))
+    (node / "cpulist").write_text(",".join(str(c) for c in allowed[:2]) + "\n")
+    before = os.sched_getaffinity(0)
+    try:
+        msg = pd.bind_to_gpu_numa_node(0, sysfs=str(tmp_path))
+        assert "node 1" in msg and os.sched_getaffinity(0) == set(allowed[:2])
+    finally:
+        os.sched_setaffinity(0, before)
+    (node / "cpulist").write_text("9999\n")
+    assert "no allowed cpus" in pd.bind_to_gpu_numa_node(0, sysfs=str(tmp_path))
+
+
+def test_postprocessing_direction_aliases():
+    from pseudo_3d_interpolation_b200 import cube_postprocessing_3D as pp
+    a = pp.footprint_filter((40, 60), sigma=2, direction="iline")
+    b = pp.footprint_filter((40, 60), sigma=2, direction="xline", dims=("xline", "iline"))       # swapped dims: same stencil
+    assert np.array_equal(a, b)
+    t = pp.footprint_filter((40, 60), sigma=2, direction="twt")                                    # ny < nx -> horizontal
+    assert np.array_equal(t, a)
+    assert not np.array_equal(a, pp.footprint_filter((40, 60), sigma=2, direction="xline"))
+    f = pp.antialiasing_filter((64, 48), "xline", {"iline": 1, "xline": 4}, sigma=2)
+    assert f.shape == (64, 48) and abs(f.min() - 1e-3) < 1e-12 and abs(f.max() - 1.0) < 1e-12
+
+
+def test_band_bounds_cover_everything():
+    for n, w in ((1025, 8), (7, 3), (1, 2), (0, 4), (5, 5)):
+        b = pocs.band_bounds(n, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) == -(-n // w) and min(sizes) >= 0          # ceil split (SURVEY 8e): nobody gets more than ceil(n / w)
