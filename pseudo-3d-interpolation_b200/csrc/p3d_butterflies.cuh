@@ -239,6 +239,11 @@ template <int DIR, typename T> struct Bfly<9, DIR, T>  { __device__ __forceinlin
 template <int DIR, typename T> struct Bfly<10, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<2, 5, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<12, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<4, 3, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<16, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyCT<4, 4, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<14, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<2, 7, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<15, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<3, 5, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<18, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<2, 9, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<21, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<3, 7, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Bfly<22, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<2, 11, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<30, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<5, 6, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Bfly<20, DIR, T> { __device__ __forceinline__ static void run(Cx<T>* v) { BflyPFA<4, 5, DIR, T>::run(v); } };
 

@@ -72,7 +72,8 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             break;
         default:
             rader_register_cols(k, n_iline, variant);
-            if (!k.cols_iter && !more_register_cols(k, n_iline)) mix_register_cols(k, n_iline);
+            if (!k.cols_iter && !more_register_cols(k, n_iline) && !mix_register_cols(k, n_iline) && !mix2_register_cols(k, n_iline))
+                mix3_register_cols(k, n_iline);
             break;
     }
     switch (n_xline) {      // row transforms have the length of the xline axis
@@ -108,7 +109,7 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else P3D_ROWS(LP200, 3, 12, "spec<200,E20,10x20,RB3>");
             break;
         default:
-            if (!more_register_rows(k, n_xline)) mix_register_rows(k, n_xline);
+            if (!more_register_rows(k, n_xline) && !mix_register_rows(k, n_xline) && !mix2_register_rows(k, n_xline)) mix3_register_rows(k, n_xline);
             break;
     }
     return k;

@@ -27,11 +27,15 @@ struct SpecKernels {
 
 // prime iline counts handled by Rader's algorithm (p3d_pocs_rader.cu); no-op for other lengths
 void rader_register_cols(SpecKernels& k, int n_iline, int variant);
-// further lengths with register plans (p3d_pocs_spec_more.cu, p3d_pocs_spec_mix.cu); false when the length has none
+// further lengths with register plans (p3d_pocs_spec_more.cu, p3d_pocs_spec_mix*.cu); false when the length has none
 bool more_register_cols(SpecKernels& k, int n_iline);
 bool more_register_rows(SpecKernels& k, int n_xline);
 bool mix_register_cols(SpecKernels& k, int n_iline);
 bool mix_register_rows(SpecKernels& k, int n_xline);
+bool mix2_register_cols(SpecKernels& k, int n_iline);
+bool mix2_register_rows(SpecKernels& k, int n_xline);
+bool mix3_register_cols(SpecKernels& k, int n_iline);
+bool mix3_register_rows(SpecKernels& k, int n_xline);
 
 SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant = 0);
 
