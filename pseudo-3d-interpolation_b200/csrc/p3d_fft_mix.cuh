@@ -60,6 +60,7 @@ template <int N_, int Ra, int Rb> struct MixPlan3 {
         // ---- pass 1: radix Ra, Ns = 1, butterfly b = j on the register set
         Bfly<Ra, DIR, F>::run(v);
         {
+            acc.pre_sync();
             Cx<F>* w = acc.line(BUF0) + (j * (Ra + D1)) * S;
 #pragma unroll
             for (int r = 0; r < Ra; ++r) w[r * S] = v[r];

@@ -125,6 +125,7 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
         if constexpr (!last) {
             static_assert(TT % B == 0 || B % TT == 0, "threads per line and Stockham block must nest");
             Cx<T>* line = acc.line(BUF);
+            acc.pre_sync();          // single-buffered accessors: the previous exchange's reads must be over
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 Cx<T>* w = line + wbase[q] * S;
@@ -180,11 +181,21 @@ template <typename T, int C, int LINE> struct ColAcc {
     Cx<T>* base;   // already offset by c
     __device__ __forceinline__ Cx<T>* line(int buf) const { return base + buf * (LINE * C); }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void pre_sync() const {}
+};
+// one buffer instead of two (half the shared memory, one more barrier per exchange)
+template <typename T, int C, int LINE> struct ColAcc1 {
+    static constexpr int STRIDE = C;
+    Cx<T>* base;
+    __device__ __forceinline__ Cx<T>* line(int) const { return base; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void pre_sync() const { __syncthreads(); }
 };
 template <typename T, int RB, int LINE> struct RowAcc {
     static constexpr int STRIDE = 1;
     Cx<T>* base;   // already offset by the row
     __device__ __forceinline__ Cx<T>* line(int buf) const { return base + buf * (RB * LINE); }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void pre_sync() const {}
 };
 }  // namespace p3d

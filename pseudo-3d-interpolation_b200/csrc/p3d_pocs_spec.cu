@@ -51,6 +51,9 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else if (variant == 4) P3D_COLS_BULK(LP1000, 4, 2, "spec<1000,E10,10x10x10,C4,2cta,cp.async>");
             else if (variant == 5) P3D_COLS_BULK(LP1000E20, 8, 1, "spec<1000,E20,10x10x10,C8,1cta,cp.async>");
             else if (variant == 6) P3D_COLS_BULK(LP1000E20, 2, 4, "spec<1000,E20,10x10x10,C2,4cta,cp.async>");
+            else if (variant == 7) { P3D_COLS_BULK(LP1000E20, 4, 4, "spec<1000,E20,10x10x10,C4,4cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000E20, 4, 4, true, float, true>; }
+            else if (variant == 8) { P3D_COLS_BULK(LP1000E20, 4, 3, "spec<1000,E20,10x10x10,C4,3cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000E20, 4, 3, true, float, true>; }
+            else if (variant == 9) { P3D_COLS_BULK(LP1000E20, 8, 2, "spec<1000,E20,10x10x10,C8,2cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000E20, 8, 2, true, float, true>; }
             else              P3D_COLS_BULK(LP1000E20, 4, 3, "spec<1000,E20,10x10x10,C4,3cta,cp.async>");
             break;
         case 2000:

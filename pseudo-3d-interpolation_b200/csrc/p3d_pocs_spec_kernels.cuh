@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstdint>
+#include <type_traits>
 
 namespace p3d {
 
@@ -31,7 +32,8 @@ __device__ __forceinline__ double warp_sum_f(double v) { return warp_sum(v); }
 // flight, so the L1 capacity left beside the exchange buffers bounded the memory-level parallelism of this kernel
 // (1000-point columns, 512 slices: 3181 us with 124 KB of L1, 4418 us with the carveout forced to 100 %); with the
 // asynchronous copies a third CTA per SM pays off (3179 -> 2594 us).
-template <typename F, typename LP, int C, int MINB, bool BULK>
+// SB: single exchange buffer (ColAcc1)
+template <typename F, typename LP, int C, int MINB, bool BULK, bool SB = false>
 __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A, const int op) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -42,7 +44,8 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     const int col = blockIdx.x * C + c;
     const bool ok = col < G.n2;
     Cx<F>* __restrict__ Ws = A.W + (long long)s * N * G.n2 + col;
-    ColAcc<F, C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<F>*>(smem_raw) + c;
+    typename std::conditional<SB, ColAcc1<F, C, LP::LINE>, ColAcc<F, C, LP::LINE>>::type acc;
+    acc.base = reinterpret_cast<Cx<F>*>(smem_raw) + c;
 
     Cx<F> v[E];
     constexpr int CHUNKS = (C * (int)sizeof(Cx<F>)) / 16;                 // 16-byte pieces per row segment
@@ -51,7 +54,7 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
                       ((reinterpret_cast<uintptr_t>(A.W) % 16) == 0);
     if (bulk) {
         const char* src0 = reinterpret_cast<const char*>(A.W + (long long)s * N * G.n2 + blockIdx.x * C);
-        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(reinterpret_cast<Cx<F>*>(smem_raw) + (size_t)LP::LINE * C);
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(reinterpret_cast<Cx<F>*>(smem_raw) + (SB ? (size_t)0 : (size_t)LP::LINE * C));
         for (int q = tid; q < N * CHUNKS; q += T * C) {
             const int row = q / CHUNKS, part = q - row * CHUNKS;
             const char* src = src0 + (long long)row * G.n2 * sizeof(Cx<F>) + part * 16;
@@ -309,16 +312,16 @@ __global__ void k_pack_mask(const uint8_t* __restrict__ mask, uint32_t* __restri
 }
 
 // ---- registry ----------------------------------------------------------------------------------------
-template <typename LP, int C, int MINB, bool BULK = false, typename F = float>
+template <typename LP, int C, int MINB, bool BULK = false, typename F = float, bool SB = false>
 static void launch_cols(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A, int ns, int op, cudaStream_t st) {
-    constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<F>);
+    constexpr size_t smem = (size_t)(SB ? 1 : 2) * LP::LINE * C * sizeof(Cx<F>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_cols_spec<F, LP, C, MINB, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cols_spec<F, LP, C, MINB, BULK, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n2 + C - 1) / C, ns);
-    k_cols_spec<F, LP, C, MINB, BULK><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
+    k_cols_spec<F, LP, C, MINB, BULK, SB><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
 }
 template <typename LP, int RB, int MINB, bool PF = false, typename F = float>
 static void launch_rows(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A, int ns, cudaStream_t st) {
