@@ -629,7 +629,10 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
         // enough (>= ~48 MB of slices) to fill the GPU
         const int64_t ne_ = (int64_t)P->n1 * P->n2;
         const int64_t min_chunk = std::max<int64_t>(1, std::min<int64_t>(n_slices, (int64_t)(48e6 / (8.0 * (double)ne_)) + 1));
-        want = std::max<int64_t>(min_chunk, (n_slices + 4 * lanes - 1) / (4 * lanes));
+        // full-size chunks: ~2 per lane; the first and last chunks of a call are shorter (ramp below), so the
+        // un-overlapped first H2D / last D2H stay short while the bulk of the launches is large enough to keep
+        // the tail of a launch (its last, partially filled wave of CTAs) small
+        want = std::max<int64_t>(min_chunk, (n_slices + 2 * lanes - 1) / (2 * lanes));
     }
     if (P->max_slices > 0) want = std::min<int64_t>(want, P->max_slices);
     int64_t have = 0;
@@ -652,11 +655,24 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
         R.dmbits = pack_mask(P, R.dmask, n_masks, P->lanes[0].stream);
     }
 
+    // chunk sizes: cap/4, cap/2, cap, ..., cap, cap/2, cap/4 (host data on several lanes), else cap
+    std::vector<int64_t> sizes;
+    if (lanes > 1 && cap >= 8 && n_slices >= 3 * cap) {
+        const int64_t ramp[2] = {std::max<int64_t>(1, cap / 4), std::max<int64_t>(1, cap / 2)};
+        int64_t left = n_slices - 2 * (ramp[0] + ramp[1]);
+        sizes.push_back(ramp[0]); sizes.push_back(ramp[1]);
+        while (left > 0) { const int64_t c = std::min<int64_t>(cap, left); sizes.push_back(c); left -= c; }
+        sizes.push_back(ramp[1]); sizes.push_back(ramp[0]);
+    } else {
+        for (int64_t first = 0; first < n_slices; first += cap) sizes.push_back(std::min<int64_t>(cap, n_slices - first));
+    }
     int li = 0;
-    for (int64_t first = 0; first < n_slices; first += cap) {
+    int64_t first = 0;
+    for (const int64_t count : sizes) {
         Lane& L = P->lanes[li];
         collect_lane(R, L);
-        process_chunk(R, L, first, std::min<int64_t>(cap, n_slices - first));
+        process_chunk(R, L, first, count);
+        first += count;
         li = (li + 1) % lanes;
     }
     for (int i = 0; i < lanes; ++i) collect_lane(R, P->lanes[i]);
