@@ -194,6 +194,12 @@ void install_spec(p3d_plan* P, int variant) {
         P3D_CUDA(cudaMalloc(&P->spec_tw_cols, sizeof(Cx<float>) * t.size()));
         P3D_CUDA(cudaMemcpy(P->spec_tw_cols, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
     } else upload(P->spec.cols_radices, &P->spec_tw_cols);
+    if (P->spec.rows_table) {
+        if (P->spec_tw_rows) { cudaFree(P->spec_tw_rows); P->spec_tw_rows = nullptr; }
+        std::vector<Cx<float>> t = P->spec.rows_table();
+        P3D_CUDA(cudaMalloc(&P->spec_tw_rows, sizeof(Cx<float>) * t.size()));
+        P3D_CUDA(cudaMemcpy(P->spec_tw_rows, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    } else
     upload(P->spec.rows_radices, &P->spec_tw_rows);
     P->d_mbits_words = 0;           // layout may have changed: repack on the next run
 }

@@ -188,7 +188,9 @@ static int primitive_root(int p) {
     return -1;
 }
 
-template <typename MP, int P> static std::vector<Cx<float>> rader_tables() {
+// ROWS = false: kernels of the column pass (forward DFT first: B = FFT(w^(g^-t)), B2 = FFT(conj(w)^(g^t)));
+// ROWS = true: kernels of the row pass (inverse DFT first: B = FFT(conj(w)^(g^-t)), B2 = FFT(w^(g^t)))
+template <typename MP, int P, bool ROWS = false> static std::vector<Cx<float>> rader_tables() {
     constexpr int M = P - 1;
     int rad[3]; MP::radices(rad);
     std::vector<Cx<float>> t = spec_twiddle_table(std::vector<int>(rad, rad + 3));
@@ -201,8 +203,9 @@ template <typename MP, int P> static std::vector<Cx<float>> rader_tables() {
     typedef std::complex<double> cd;
     std::vector<cd> bf(M), bi(M);
     for (int q = 0; q < M; ++q) {
-        bf[q] = std::polar(1.0, -2.0 * M_PI * (double)kperm[q] / (double)P);      // w^(g^-q)
-        bi[q] = std::polar(1.0, +2.0 * M_PI * (double)perm[q] / (double)P);       // conj(w)^(g^q)
+        const double sg = ROWS ? -1.0 : 1.0;
+        bf[q] = std::polar(1.0, -sg * 2.0 * M_PI * (double)kperm[q] / (double)P);      // w^(g^-q)       (rows: conjugate)
+        bi[q] = std::polar(1.0, +sg * 2.0 * M_PI * (double)perm[q] / (double)P);       // conj(w)^(g^q)  (rows: conjugate)
     }
     // M-point DFTs of the two kernels (once per plan: M^2 = 1.44 M complex multiplies), scaled by 1/M
     std::vector<cd> wM(M);
@@ -243,6 +246,132 @@ static void launch_rader_stats(const PocsGeom& G, const Cx<float>* tab, const Ba
 
 typedef MixPlan3<1200, 10, 12> MP1200;
 typedef MixPlan3<1200, 20, 3> MP1200E20;
+
+// ---- row pass for a prime xline count -------------------------------------------------------------------------
+// One row per CTA.  The row of W (and of the observed data) is staged in shared memory in natural order by coalesced
+// loads; the Rader permutation is the gather from there.  Inverse DFT first (kernel conj(w)): slot m of the result
+// holds y[g^-m], so the re-insertion reads d and the mask at n = kperm[m]; the forward DFT takes h[m] = x[g^-m] as it
+// is and leaves X[g^s] in slot s, which goes back through shared memory to a coalesced store.
+template <typename MP, int P, int MINB>
+__global__ void __launch_bounds__(MP::T, MINB)
+k_rows_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tab, const __grid_constant__ BandArgs<float> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_s[32];
+    constexpr int E = MP::E, T = MP::T, M = MP::N;
+    static_assert(M == P - 1 && MP::LINE >= P, "Rader rows: convolution length P - 1, staging fits an exchange buffer");
+    const Cx<float>* __restrict__ tw = tab;
+    const Cx<float>* __restrict__ B1 = tab + (T + M);
+    const Cx<float>* __restrict__ B2 = B1 + M;
+    const int* __restrict__ perm = reinterpret_cast<const int*>(B2 + M);
+    const int* __restrict__ kperm = perm + M;
+    const int s = blockIdx.y, row = blockIdx.x, j = threadIdx.x;
+    const int stopped = A.stop[s];
+    const long long base = ((long long)s * G.n1 + row) * P;
+    Cx<float>* __restrict__ Wp = A.W + base;
+    const Cx<float>* __restrict__ Dp = A.D + base;
+    Cx<float>* __restrict__ Op = A.OUT + base;
+    RowAcc<float, 1, MP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw);
+    Cx<float>* land = acc.line(1);                                       // W row, natural order (free until exchange 2)
+    Cx<float>* dst = reinterpret_cast<Cx<float>*>(smem_raw) + 2 * MP::LINE;   // observed row, natural order
+    for (int i = j; i < P; i += T) { land[i] = Wp[i]; dst[i] = Dp[i]; }
+    if (stopped != 0) return;
+    __syncthreads();
+
+    Cx<float> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = land[__ldg(perm + j + e * T)];
+    Cx<float> dc = land[0];
+
+    // ---- inverse DFT of length P (unscaled)
+    MP::template fft<-1, 0, float>(v, acc, j, tw);
+    {
+        const Cx<float> w0 = dc;
+        if (j == 0) dc = cadd(w0, v[0]);                 // y[0]
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], ldg_cx(B1 + j + e * T));
+        if (j == 0) v[0] = cadd(v[0], w0);
+    }
+    MP::template fft<+1, 0, float>(v, acc, j, tw);
+    // v[e] = y[kperm[j + e*T]], dc = y[0] (thread 0)
+
+    // ---- re-insertion at the natural positions, norm
+    const long long mrow = (((A.first_slice + s) / G.slices_per_mask) * G.n1 + row) * (long long)P;
+    float part = 0.f;
+    auto reinsert = [&](Cx<float> y, const int n) {
+        const Cx<float> d = dst[n];
+        const float m = (float)A.mask[mrow + n];
+        const float coef = (1.f - A.alpha * m) * A.inv_n;
+        Cx<float> x = cmake<float>(fmaf(coef, y.x, A.alpha * d.x), fmaf(coef, y.y, A.alpha * d.y));
+        part += sqrtf(x.x * x.x + x.y * x.y);
+        if (A.write_out) Op[n] = x;
+        if (A.adaptive) {
+            const float keep = 1.f - A.alpha * m, om = 1.f - A.alpha;
+            const Cx<float> xt = cmake<float>(A.alpha * d.x + keep * x.x, A.alpha * d.y + keep * x.y);
+            x = cmake<float>(xt.x + om * (d.x - m * x.x), xt.y + om * (d.y - m * x.y));
+        }
+        return x;
+    };
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = reinsert(v[e], __ldg(kperm + j + e * T));
+    if (j == 0) dc = reinsert(dc, 0);
+    double dp = warp_sum((double)part);
+    if ((j & 31) == 0) red_s[j >> 5] = dp;
+    __syncthreads();
+    if (j < 32) {
+        constexpr int NW = (T + 31) / 32;
+        double t = j < NW ? red_s[j] : 0.0;
+        t = warp_sum(t);
+        if (j == 0) atomicAdd(&A.S[(long long)s * (A.niter + 1) + A.k + 1], t);
+    }
+    if (A.last) return;
+
+    // ---- forward DFT of length P: h[m] = x[g^-m] is the register order
+    MP::template fft<-1, 0, float>(v, acc, j, tw);
+    {
+        const Cx<float> x0 = dc;
+        if (j == 0) dc = cadd(x0, v[0]);                 // X[0]
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], ldg_cx(B2 + j + e * T));
+        if (j == 0) v[0] = cadd(v[0], x0);
+    }
+    MP::template fft<+1, 0, float>(v, acc, j, tw);
+    // v[e] = X[perm[j + e*T]]: back to natural order through exchange buffer 0 (last read before the second barrier
+    // of the transform above), coalesced store
+    Cx<float>* st = acc.line(0);
+#pragma unroll
+    for (int e = 0; e < E; ++e) st[__ldg(perm + j + e * T)] = v[e];
+    if (j == 0) st[0] = dc;
+    __syncthreads();
+    for (int i = j; i < P; i += T) Wp[i] = st[i];
+}
+
+template <typename MP, int P, int MINB>
+static void launch_rows_rader(const PocsGeom& G, const Cx<float>* tab, const BandArgs<float>& A, int ns, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(2 * MP::LINE + P) * sizeof(Cx<float>);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_rows_rader<MP, P, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid(G.n1, ns);
+    k_rows_rader<MP, P, MINB><<<grid, MP::T, smem, st>>>(G, tab, A);
+}
+
+void rader_register_rows(SpecKernels& k, int n_xline, int variant) {
+    if (n_xline != 1201) return;
+    if (variant == 1) {
+        k.rows_iter = launch_rows_rader<MP1200E20, 1201, 6>;
+        k.rows_name = "rader<1201,20x3x20,RB1>";
+        k.rows_radices = {20, 3, 20};
+        k.rows_table = rader_tables<MP1200E20, 1201, true>;
+    } else {
+        k.rows_iter = launch_rows_rader<MP1200, 1201, 6>;
+        k.rows_name = "rader<1201,10x12x10,RB1>";
+        k.rows_radices = {10, 12, 10};
+        k.rows_table = rader_tables<MP1200, 1201, true>;
+    }
+    k.rows_init = nullptr; k.pack_mask = nullptr; k.rows_T = 0;       // generic row FFT of the observed slice, byte mask
+}
 
 void rader_register_cols(SpecKernels& k, int n_iline, int variant) {
     if (n_iline != 1201) return;

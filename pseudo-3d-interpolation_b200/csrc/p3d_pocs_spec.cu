@@ -68,6 +68,7 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else if (variant == 3) P3D_COLS_BULK(LP256, 16, 3, "spec<256,E16,16x16,C16,cp.async>");
             else              P3D_COLS_BULK(LP256, 8, 6, "spec<256,E16,16x16,C8,6cta,cp.async>");
             break;
+        case 847:  P3D_COLS_BULK(MP847, 4, 3, "mix<847,11x7x11,C4,cp.async>"); break;
         case 200:
             if (variant == 1) P3D_COLS(LP200, 16, 4, "spec<200,E20,10x20,C16>");
             else if (variant == 2) P3D_COLS_BULK(LP200, 16, 5, "spec<200,E20,10x20,C16,5cta,cp.async>");
@@ -112,7 +113,9 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
             else P3D_ROWS(LP200, 3, 12, "spec<200,E20,10x20,RB3>");
             break;
         default:
-            if (!more_register_rows(k, n_xline) && !mix_register_rows(k, n_xline) && !mix2_register_rows(k, n_xline)) mix3_register_rows(k, n_xline);
+            rader_register_rows(k, n_xline, variant);
+            if (!k.rows_iter && !more_register_rows(k, n_xline) && !mix_register_rows(k, n_xline) && !mix2_register_rows(k, n_xline))
+                mix3_register_rows(k, n_xline);
             break;
     }
     return k;

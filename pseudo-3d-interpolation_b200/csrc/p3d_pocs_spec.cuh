@@ -23,10 +23,12 @@ struct SpecKernels {
     int rows_T = 0;                                 // threads per row line (packed-mask layout)
     // optional: builder of the column kernels' whole table buffer (twiddles + algorithm tables, e.g. Rader's)
     std::vector<Cx<float>> (*cols_table)() = nullptr;
+    std::vector<Cx<float>> (*rows_table)() = nullptr;
 };
 
 // prime iline counts handled by Rader's algorithm (p3d_pocs_rader.cu); no-op for other lengths
 void rader_register_cols(SpecKernels& k, int n_iline, int variant);
+void rader_register_rows(SpecKernels& k, int n_xline, int variant);
 // further lengths with register plans (p3d_pocs_spec_more.cu, p3d_pocs_spec_mix*.cu); false when the length has none
 bool more_register_cols(SpecKernels& k, int n_iline);
 bool more_register_rows(SpecKernels& k, int n_xline);

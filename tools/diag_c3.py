@@ -9,7 +9,8 @@ from oracle.golden_cases import make_input
 
 def rel(a, b): return float(np.linalg.norm(a.astype(np.complex128) - b) / np.linalg.norm(b))
 
-shape = (1201, 48)
+import sys as _s
+shape = tuple(int(v) for v in _s.argv[1:3]) if len(_s.argv) > 2 else (1201, 48)
 for seed in (9, 10, 11):
     for op, model, alpha, version in (("garrote", "exponential", 0.7, "adaptive"), ("garrote", "exponential", 1.0, "regular"), ("soft", "exponential", 0.7, "adaptive")):
         x, mask = make_input(dict(seed=seed, shape=shape, keep=0.3, nwaves=5))
