@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define P3D_ABI_VERSION 2
+#define P3D_ABI_VERSION 3
 
 typedef enum {
     P3D_OK = 0,
@@ -90,7 +90,9 @@ int p3d_plan_destroy(p3d_plan* plan);
  *   niter_out[n_slices]          : iterations executed per slice (host, may be NULL)
  *   cost_out[n_slices]           : last cost per slice (host, may be NULL)
  *   costs_out[n_slices * niter]  : cost history, NaN-padded after the last iteration (host, may be NULL)
- * Host buffers may be pageable; pinned buffers (p3d_host_alloc) make the copies asynchronous. */
+ * Host buffers may be pageable; pinned buffers (p3d_host_alloc) make the copies asynchronous.
+ * Device buffers: x is read in place during every iteration and out is written while x is still needed, so
+ * [x, x + n) and [out, out + n) must not overlap (P3D_ERR_BAD_ARG otherwise); x is never modified. */
 int p3d_pocs_run(p3d_plan* plan, const p3d_pocs_params* params,
                  const void* x, int x_mem, const uint8_t* mask, int64_t slices_per_mask,
                  void* out, int out_mem, int64_t n_slices,
@@ -149,8 +151,9 @@ int p3d_memcpy(int device, void* dst, const void* src, int64_t bytes, int kind /
 int p3d_device_synchronize(int device);
 
 /* Per-kernel device-time accounting (CUDA events on the launch stream).
- * kinds: 0 rows_init, 1 cols_stats, 2 cols_iter, 3 rows_iter, 4 time_fft, 5 time_ifft, 6 sort, 7 fft2 */
-#define P3D_PROFILE_KINDS 8
+ * kinds: 0 rows_init, 1 cols_stats, 2 cols_iter, 3 rows_iter, 4 time_fft, 5 time_ifft, 6 sort, 7 fft2,
+ *        8 cols_iter64, 9 rows_iter64, 10 init64, 11 replay (complex128 side of the escalating-precision mode) */
+#define P3D_PROFILE_KINDS 12
 int p3d_plan_set_profiling(p3d_plan* plan, int enabled);
 int p3d_plan_get_profile(p3d_plan* plan, double* ms_per_kind, int64_t* launches_per_kind, int reset);
 /* Device-side timing of whole runs: record a CUDA event in slot (0..7) on the plan's first
@@ -160,8 +163,17 @@ int p3d_plan_event_record(p3d_plan* plan, int slot);
 int p3d_plan_event_elapsed_ms(p3d_plan* plan, int slot_a, int slot_b, double* ms);
 /* Human-readable description of the chosen kernels / tiles / bands (for DESIGN.md and bench). */
 int p3d_plan_describe(p3d_plan* plan, char* buf, int64_t buflen);
-/* Tuning knobs (mostly for experiments): key in {"band_slices","force_generic","lanes"} */
+/* Options: key in {"band_slices","force_generic","lanes","max_slices","spec_variant","spec_variant64",
+ *   "precision"    0 (default) = escalating: a slice iterates in fp32 until a coefficient of its spectrum comes within the
+ *                  guard band of the threshold, and in complex128 from that iterate on (meets the 1e-4 of the float64
+ *                  reference at about 60 % of the fp32 rate); 32 = fp32 only (fastest; hard-threshold decisions may
+ *                  differ from float64 once tau_k reaches the dense part of the spectrum); 64 = complex128 throughout,
+ *   "guard_factor" half-width of the guard band in units of 2^-24 * rms|X| (default 1024; 0 disables the switch),
+ *   "seg_iters"    iterations between two compactions of the fp32 slice list (default 4)} */
 int p3d_plan_set_option(p3d_plan* plan, const char* key, int64_t value);
+/* Escalating mode, last p3d_pocs_run of this plan: slices that switched to complex128 and the slice-iterations they
+ * ran there (either pointer may be NULL). */
+int p3d_plan_get_escalation(p3d_plan* plan, int64_t* n_slices, int64_t* n_slice_iterations);
 
 #ifdef __cplusplus
 }

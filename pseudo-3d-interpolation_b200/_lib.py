@@ -19,7 +19,8 @@ MEM_HOST, MEM_DEVICE = 0, 1
 OPS = {"hard": 0, "soft": 1, "garrote": 2, "garotte": 2}
 MODELS = {"linear": 0, "exponential": 1, "data-driven": 2, "inverse_proportional": 3}
 VERSIONS = {"regular": 0, "fast": 1, "adaptive": 2}
-PROFILE_KINDS = ("rows_init", "cols_stats", "cols_iter", "rows_iter", "time_fft", "time_ifft", "sort", "fft2")
+PROFILE_KINDS = ("rows_init", "cols_stats", "cols_iter", "rows_iter", "time_fft", "time_ifft", "sort", "fft2",
+                 "cols_iter64", "rows_iter64", "init64", "replay")
 
 
 class PocsParams(C.Structure):
@@ -67,6 +68,7 @@ SIGNATURES = {
     "p3d_plan_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "p3d_plan_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "p3d_plan_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "p3d_plan_get_escalation": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
 

@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <string>
+#include <thread>
 
 using namespace p3d;
 
@@ -35,6 +37,19 @@ struct Lane {
     Cx<float>* h_tau = nullptr; double* h_S = nullptr; int* h_stop = nullptr; SliceStats* h_stats = nullptr;
     // pending chunk (results not yet collected)
     bool pending = false; int64_t p_first = 0, p_count = 0;
+    // escalating-precision mode: complex128 state of the slices that left the fp32 path, per-slice switch flags
+    bool has_esc = false;
+    Cx<double>* W64 = nullptr; Cx<double>* tau64 = nullptr; Cx<double>* h_tau64 = nullptr;
+    int* esc = nullptr; int* h_esc = nullptr;
+    float* guard = nullptr; float* h_guard = nullptr;
+    int* list = nullptr; int* h_list = nullptr;
+    double2* cand = nullptr; int cand_stride = 0;
+    unsigned* arena = nullptr; int* acnt = nullptr; int* astart = nullptr; int* h_astart = nullptr; double2* yval = nullptr;
+    int arena_cap = 0;
+    int64_t n_escalated = 0, n_esc_iters = 0;
+    // CUB scratch of the data-driven schedule (per lane: lanes sort concurrently on their own streams)
+    void* cub_temp = nullptr; size_t cub_temp_bytes = 0;
+    std::vector<EventPair> events;      // profiling events of this lane's launches
 };
 
 }  // namespace
@@ -51,7 +66,14 @@ struct p3d_plan {
     SpecKernels spec{};              // specialised register-resident kernels when available
     bool force_generic = false;
     int spec_variant64 = 0;
-    int precision = 32;              // 32: fp32 fast path, 64: float64 state mode (p3d_pocs_f64.cu)
+    int precision = 0;               // 0: escalating (fp32 state, complex128 once a coefficient enters the guard band of the
+                                     // threshold), 32: fp32 only, 64: float64 state mode (p3d_pocs_f64.cu)
+    double guard_factor = 1024.0;    // guard half-width in units of eps32 * rms|X| (escalating mode)
+    int seg_iters = 4;               // escalating mode: iterations between two compactions of the active-slice list
+    int arena_cap = 16384;           // escalating mode: support-record entries per slice (all pilot iterations together)
+    Cx<double>* mhat = nullptr; int64_t mhat_masks = 0;          // fft2 of the mask planes in complex128 (exact restart)
+    Cx<float>* mask_c64 = nullptr; SliceStats* mh_stats = nullptr; double2* mh_cand = nullptr; int mh_cand_stride = 0;
+    int64_t n_escalated = 0, n_esc_iters = 0;   // statistics of the last run (escalating mode)
     F64Runner* f64 = nullptr;
     int64_t max_slices = 0;
     int band_slices = 0;
@@ -82,26 +104,30 @@ struct DeviceGuard {
     ~DeviceGuard() { cudaSetDevice(prev); }
 };
 
-void prof_begin(p3d_plan* P, cudaStream_t st, int kind) {
+void prof_begin(p3d_plan* P, std::vector<EventPair>& ev, cudaStream_t st, int kind) {
     if (!P->profiling) return;
     EventPair e; e.kind = kind;
     cudaEventCreate(&e.a); cudaEventCreate(&e.b);
     cudaEventRecord(e.a, st);
-    P->events.push_back(e);
+    ev.push_back(e);
 }
-void prof_end(p3d_plan* P, cudaStream_t st) {
+void prof_end(p3d_plan* P, std::vector<EventPair>& ev, cudaStream_t st) {
     if (!P->profiling) return;
-    cudaEventRecord(P->events.back().b, st);
+    cudaEventRecord(ev.back().b, st);
 }
-void prof_collect(p3d_plan* P) {
-    for (auto& e : P->events) {
+void prof_collect_vec(p3d_plan* P, std::vector<EventPair>& ev) {
+    for (auto& e : ev) {
         float ms = 0.f;
         if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
             P->prof_ms[e.kind] += ms; P->prof_n[e.kind] += 1;
         }
         cudaEventDestroy(e.a); cudaEventDestroy(e.b);
     }
-    P->events.clear();
+    ev.clear();
+}
+void prof_collect(p3d_plan* P) {
+    prof_collect_vec(P, P->events);
+    for (auto& L : P->lanes) prof_collect_vec(P, L.events);
 }
 
 void free_lane(Lane& L) {
@@ -116,19 +142,41 @@ void free_lane(Lane& L) {
     if (L.h_S) cudaFreeHost(L.h_S);
     if (L.h_stop) cudaFreeHost(L.h_stop);
     if (L.h_stats) cudaFreeHost(L.h_stats);
+    if (L.W64) cudaFree(L.W64);
+    if (L.tau64) cudaFree(L.tau64);
+    if (L.esc) cudaFree(L.esc);
+    if (L.guard) cudaFree(L.guard);
+    if (L.list) cudaFree(L.list);
+    if (L.cand) cudaFree(L.cand);
+    if (L.arena) cudaFree(L.arena);
+    if (L.acnt) cudaFree(L.acnt);
+    if (L.astart) cudaFree(L.astart);
+    if (L.yval) cudaFree(L.yval);
+    if (L.h_astart) cudaFreeHost(L.h_astart);
+    L.arena = nullptr; L.acnt = nullptr; L.astart = nullptr; L.yval = nullptr; L.h_astart = nullptr; L.arena_cap = 0;
+    if (L.h_tau64) cudaFreeHost(L.h_tau64);
+    if (L.h_esc) cudaFreeHost(L.h_esc);
+    if (L.h_guard) cudaFreeHost(L.h_guard);
+    if (L.h_list) cudaFreeHost(L.h_list);
+    if (L.cub_temp) cudaFree(L.cub_temp);
+    L.cub_temp = nullptr; L.cub_temp_bytes = 0; L.cand_stride = 0;
+    L.W64 = L.tau64 = L.h_tau64 = nullptr; L.esc = L.h_esc = L.list = L.h_list = nullptr; L.guard = L.h_guard = nullptr; L.cand = nullptr;
+    L.has_esc = false;
     L.W = L.D = L.OUT = L.tau = nullptr; L.S = nullptr; L.stop = nullptr; L.stats = nullptr;
     L.h_tau = nullptr; L.h_S = nullptr; L.h_stop = nullptr; L.h_stats = nullptr;
     L.cap = 0; L.niter_cap = 0; L.own_d = L.own_out = false;
 }
 
-void ensure_lane(p3d_plan* P, Lane& L, int64_t cap, int niter, bool need_d, bool need_out) {
+void ensure_lane(p3d_plan* P, Lane& L, int64_t cap, int niter, bool need_d, bool need_out, bool need_esc, int cand_stride) {
     const int64_t ne = (int64_t)P->n1 * P->n2;
     if (!L.stream) P3D_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-    const bool regrow = cap > L.cap || niter > L.niter_cap || (need_d && !L.own_d) || (need_out && !L.own_out);
+    const bool regrow = cap > L.cap || niter > L.niter_cap || (need_d && !L.own_d) || (need_out && !L.own_out) ||
+                        (need_esc && (!L.has_esc || cand_stride > L.cand_stride || P->arena_cap != L.arena_cap));
     if (!regrow) return;
     cudaStream_t st = L.stream;
     cap = std::max(cap, L.cap); niter = std::max(niter, L.niter_cap);
-    need_d = need_d || L.own_d; need_out = need_out || L.own_out;
+    need_d = need_d || L.own_d; need_out = need_out || L.own_out; need_esc = need_esc || L.has_esc;
+    cand_stride = std::max(cand_stride, L.cand_stride);
     L.stream = nullptr; free_lane(L); L.stream = st;
     P3D_CUDA(cudaMalloc(&L.W, sizeof(Cx<float>) * ne * cap));
     if (need_d) { P3D_CUDA(cudaMalloc(&L.D, sizeof(Cx<float>) * ne * cap)); L.own_d = true; }
@@ -141,6 +189,25 @@ void ensure_lane(p3d_plan* P, Lane& L, int64_t cap, int niter, bool need_d, bool
     P3D_CUDA(cudaMallocHost(&L.h_S, sizeof(double) * cap * (niter + 1)));
     P3D_CUDA(cudaMallocHost(&L.h_stop, sizeof(int) * cap));
     P3D_CUDA(cudaMallocHost(&L.h_stats, sizeof(SliceStats) * cap));
+    P3D_CUDA(cudaMalloc(&L.list, sizeof(int) * cap));
+    P3D_CUDA(cudaMallocHost(&L.h_list, sizeof(int) * cap));
+    if (need_esc) {
+        P3D_CUDA(cudaMalloc(&L.W64, sizeof(Cx<double>) * ne * cap));
+        P3D_CUDA(cudaMalloc(&L.tau64, sizeof(Cx<double>) * cap * niter));
+        P3D_CUDA(cudaMalloc(&L.esc, sizeof(int) * cap));
+        P3D_CUDA(cudaMalloc(&L.guard, sizeof(float) * cap));
+        P3D_CUDA(cudaMalloc(&L.cand, sizeof(double2) * cap * std::max(1, cand_stride)));
+        P3D_CUDA(cudaMallocHost(&L.h_tau64, sizeof(Cx<double>) * cap * niter));
+        P3D_CUDA(cudaMallocHost(&L.h_esc, sizeof(int) * cap));
+        P3D_CUDA(cudaMallocHost(&L.h_guard, sizeof(float) * cap));
+        L.arena_cap = P->arena_cap;
+        P3D_CUDA(cudaMalloc(&L.arena, sizeof(unsigned) * cap * L.arena_cap));
+        P3D_CUDA(cudaMalloc(&L.yval, sizeof(double2) * cap * L.arena_cap));
+        P3D_CUDA(cudaMalloc(&L.acnt, sizeof(int) * cap));
+        P3D_CUDA(cudaMalloc(&L.astart, sizeof(int) * cap * (niter + 1)));
+        P3D_CUDA(cudaMallocHost(&L.h_astart, sizeof(int) * cap * (niter + 1)));
+        L.has_esc = true; L.cand_stride = std::max(1, cand_stride);
+    }
     L.cap = cap; L.niter_cap = niter;
 }
 
@@ -205,32 +272,36 @@ void install_spec(p3d_plan* P, int variant) {
 }
 
 // ---- launches -----------------------------------------------------------------------------------
-void launch_rows_init(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices) {
-    prof_begin(P, st, 0);
+void launch_rows_init(p3d_plan* P, Lane& L, const BandArgs<float>& A, int nslices) {
+    cudaStream_t st = L.stream;
+    prof_begin(P, L.events, st, 0);
     if (P->spec.rows_init && !P->force_generic) P->spec.rows_init(P->geom, P->spec_tw_rows, A, nslices, st);
     else generic_rows_init(generic_cfg(P), P->ax2.dev(), A, nslices, st);
-    prof_end(P, st);
+    prof_end(P, L.events, st);
     P3D_CUDA(cudaGetLastError());
 }
-void launch_cols_stats(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices) {
-    prof_begin(P, st, 1);
+void launch_cols_stats(p3d_plan* P, Lane& L, const BandArgs<float>& A, int nslices) {
+    cudaStream_t st = L.stream;
+    prof_begin(P, L.events, st, 1);
     if (P->spec.cols_stats && !P->force_generic) P->spec.cols_stats(P->geom, P->spec_tw_cols, A, nslices, st);
     else generic_cols_stats(generic_cfg(P), P->ax1.dev(), A, nslices, st);
-    prof_end(P, st);
+    prof_end(P, L.events, st);
     P3D_CUDA(cudaGetLastError());
 }
-void launch_cols_iter(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices, int op) {
-    prof_begin(P, st, 2);
+void launch_cols_iter(p3d_plan* P, Lane& L, const BandArgs<float>& A, int nslices, int op) {
+    cudaStream_t st = L.stream;
+    prof_begin(P, L.events, st, 2);
     if (P->spec.cols_iter && !P->force_generic) P->spec.cols_iter(P->geom, P->spec_tw_cols, A, nslices, op, st);
     else generic_cols_iter(generic_cfg(P), P->ax1.dev(), A, nslices, op, st);
-    prof_end(P, st);
+    prof_end(P, L.events, st);
     P3D_CUDA(cudaGetLastError());
 }
-void launch_rows_iter(p3d_plan* P, cudaStream_t st, const BandArgs<float>& A, int nslices) {
-    prof_begin(P, st, 3);
+void launch_rows_iter(p3d_plan* P, Lane& L, const BandArgs<float>& A, int nslices) {
+    cudaStream_t st = L.stream;
+    prof_begin(P, L.events, st, 3);
     if (P->spec.rows_iter && !P->force_generic) P->spec.rows_iter(P->geom, P->spec_tw_rows, A, nslices, st);
     else generic_rows_iter(generic_cfg(P), P->ax2.dev(), A, nslices, st);
-    prof_end(P, st);
+    prof_end(P, L.events, st);
     P3D_CUDA(cudaGetLastError());
 }
 
@@ -349,7 +420,7 @@ void percentile_thresholds(p3d_plan* P, cudaStream_t st, const BandArgs<float>& 
         P->cub_temp = nullptr; P->cub_temp_bytes = 0;
         P3D_CUDA(cudaMalloc(&P->cub_temp, need)); P->cub_temp_bytes = need;
     }
-    prof_begin(P, st, 6);
+    prof_begin(P, P->events, st, 6);
     for (int64_t s0 = 0; s0 < nb; s0 += P->pct_slices) {
         const int cnt = (int)std::min<int64_t>(P->pct_slices, nb - s0);
         P3D_CUDA(cudaMemcpyAsync(P->pct_scr, B.W + s0 * ne, sizeof(Cx<float>) * ne * cnt, cudaMemcpyDeviceToDevice, st));
@@ -361,13 +432,15 @@ void percentile_thresholds(p3d_plan* P, cudaStream_t st, const BandArgs<float>& 
             k_pick_percentile<<<1, 1, 0, st>>>(P->pct_sorted, ne, const_cast<Cx<float>*>(B.tau) + (s0 + i) * B.niter + k);
         }
     }
-    prof_end(P, st);
+    prof_end(P, P->events, st);
     P3D_CUDA(cudaGetLastError());
 }
 
 struct RunCtx {
     p3d_plan* P; const p3d_pocs_params* pr;
     const Cx<float>* x; int x_mem; const uint8_t* dmask; const uint32_t* dmbits; int64_t spm;
+    const uint32_t* dmbits64 = nullptr;     // packed mask of the complex128 row kernel (escalating mode)
+    bool escalate = false;
     Cx<float>* out; int out_mem;
     int32_t* niter_out; double* cost_out; double* costs_out;
     double* tau_out;            // schedule-only mode
@@ -445,10 +518,10 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             B.W = L.W + b0 * ne; B.D = D + b0 * ne; B.OUT = OUT + b0 * ne; B.first_slice = 0;
             B.tau = L.tau + b0 * niter; B.S = L.S + b0 * (niter + 1); B.stop = L.stop + b0; B.stats = L.stats + b0;
             B.adaptive = 0; B.accum = 0; B.store_x0 = 0;
-            launch_rows_init(P, st, B, nb);
+            launch_rows_init(P, L, B, nb);
             B.k = 0; B.last = 1; B.write_out = 1;
-            launch_cols_iter(P, st, B, nb, P3D_OP_FILTER);
-            launch_rows_iter(P, st, B, nb);
+            launch_cols_iter(P, L, B, nb, P3D_OP_FILTER);
+            launch_rows_iter(P, L, B, nb);
         }
         if (R.out_mem == P3D_MEM_HOST)
             P3D_CUDA(cudaMemcpyAsync(R.out + first * ne, OUT, sizeof(Cx<float>) * ne * count, cudaMemcpyDeviceToHost, st));
@@ -475,8 +548,8 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
         const int nb = (int)std::min<int64_t>(band_max, count - b0);
         BandArgs<float> B = band_args(b0);
         B.adaptive = 0; B.accum = 1; B.store_x0 = data_driven ? 1 : 0;
-        launch_rows_init(P, st, B, nb);
-        launch_cols_stats(P, st, B, nb);
+        launch_rows_init(P, L, B, nb);
+        launch_cols_stats(P, L, B, nb);
     }
     P3D_CUDA(cudaMemcpyAsync(L.h_stats, L.stats, sizeof(SliceStats) * count, cudaMemcpyDeviceToHost, st));
     P3D_CUDA(cudaStreamSynchronize(st));
@@ -499,10 +572,10 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
         // order statistics of the candidates inside (tau_min, tau_max), per slice, on the device
         size_t need = 0;
         cub::DeviceRadixSort::SortKeysDescending(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (long long)ne, 0, 64, st);
-        if (need > P->cub_temp_bytes) {
-            if (P->cub_temp) cudaFree(P->cub_temp);
-            P->cub_temp = nullptr; P->cub_temp_bytes = 0;
-            P3D_CUDA(cudaMalloc(&P->cub_temp, need)); P->cub_temp_bytes = need;
+        if (need > L.cub_temp_bytes) {
+            if (L.cub_temp) cudaFree(L.cub_temp);
+            L.cub_temp = nullptr; L.cub_temp_bytes = 0;
+            P3D_CUDA(cudaMalloc(&L.cub_temp, need)); L.cub_temp_bytes = need;
         }
         for (int64_t i = 0; i < count; ++i) {
             L.h_stop[i] = L.h_stats[i].nnz == 0 ? -1 : 0;
@@ -513,12 +586,12 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             const unsigned long long hi = lex_key((float)tmax.real(), (float)tmax.imag());
             unsigned long long* keys = reinterpret_cast<unsigned long long*>(OUT + i * ne);
             unsigned long long* sorted = reinterpret_cast<unsigned long long*>(L.W + i * ne);
-            prof_begin(P, st, 6);
+            prof_begin(P, L.events, st, 6);
             k_make_keys<<<std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(keys, ne, lo, hi, L.stats + i);
-            size_t tb = P->cub_temp_bytes;
-            cub::DeviceRadixSort::SortKeysDescending(P->cub_temp, tb, keys, sorted, (long long)ne, 0, 64, st);
+            size_t tb = L.cub_temp_bytes;
+            cub::DeviceRadixSort::SortKeysDescending(L.cub_temp, tb, keys, sorted, (long long)ne, 0, 64, st);
             k_pick_tau<<<1, 128, 0, st>>>(sorted, L.stats + i, L.tau + i * niter, niter);
-            prof_end(P, st);
+            prof_end(P, L.events, st);
         }
         P3D_CUDA(cudaGetLastError());
         P3D_CUDA(cudaMemcpyAsync(L.h_tau, L.tau, sizeof(Cx<float>) * count * niter, cudaMemcpyDeviceToHost, st));
@@ -554,7 +627,7 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             const int nb = (int)std::min<int64_t>(band_max, count - b0);
             BandArgs<float> B = band_args(b0);
             B.adaptive = adaptive ? 1 : 0; B.accum = 0;
-            launch_rows_init(P, st, B, nb);
+            launch_rows_init(P, L, B, nb);
         }
     }
 
@@ -570,8 +643,8 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             // x_k only has to reach OUT when iteration k can be the last one executed
             B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
             if (pr.thresh_percentile) percentile_thresholds(P, st, B, nb, k);
-            launch_cols_iter(P, st, B, nb, pr.thresh_op);
-            launch_rows_iter(P, st, B, nb);
+            launch_cols_iter(P, L, B, nb, pr.thresh_op);
+            launch_rows_iter(P, L, B, nb);
         }
     }
 
@@ -581,6 +654,521 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     P3D_CUDA(cudaMemcpyAsync(L.h_S, L.S, sizeof(double) * count * (niter + 1), cudaMemcpyDeviceToHost, st));
     P3D_CUDA(cudaMemcpyAsync(L.h_stop, L.stop, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
     L.pending = true; L.p_first = first; L.p_count = count;
+}
+
+// =====================================================================================================
+// Escalating-precision engine ("precision" = 0, the default).
+//
+// The reference iterates in float64.  An fp32 iterate follows that trajectory to ~1e-7 as long as every
+// threshold decision is the same; once tau_k has sunk into the dense part of the spectrum a coefficient sits within
+// fp32 rounding of the threshold sooner or later, one decision differs and the late iterations amplify the difference
+// (1e-3 on configs 1 and 2).  Continuing in complex128 from the fp32 iterate is not enough either: the fp32 rounding the
+// iterate has collected decays by only ~10 % per iteration, so it is still there when the thresholds reach the dense
+// spectrum (measured: 20 of 1025 slices of config 2 off by more than 1e-4 even with a guard band of 4096 eps).
+//
+// So the fp32 iterations are only a PILOT that finds out which coefficients survive each threshold while the spectrum
+// is sparse, and the float64 trajectory is rebuilt exactly from that:
+//   * the column kernel tests every coefficient against a guard band | |X| - c_k | < G * eps32 * rms|X| around the
+//     modulus c_k at which the operator jumps, and appends the index of every survivor to the slice's support record;
+//   * the first guard hit (or a full record) in iteration k_e freezes the slice: iterations 0 .. k_e - 1 were decided
+//     unambiguously, iteration k_e is left to complex128;
+//   * with the supports S_i known the float64 iterates obey a linear recursion in the SPARSE domain,
+//         X_i[j] = alpha X0[j] + y_{i-1}[j] - (alpha / N) sum_{s in S_{i-1}} mhat[j - s] y_{i-1}[s],   y_i = T_i(X_i) on S_i,
+//     (mhat = fft2(mask), X0 = fft2(d), both in complex128): |S_i| |S_{i-1}| complex multiply-adds per iteration
+//     instead of two 2-D FFTs (k_replay);
+//   * y_{k_e - 1} is scattered into a zeroed spectrum, one complex128 inverse column pass + row pass rebuild
+//     x_{k_e - 1} and its row FFT exactly, and the complex128 iteration kernels run iterations k_e .. niter - 1.
+// The schedule needs the lexicographic maximum of X0 to double accuracy as well (tau = p * z), so the statistics pass
+// runs in complex128 and leaves X0 in the complex128 work array for the replay.
+// Phase 1 (fp32) runs in segments of seg_iters iterations over a compacted list of the slices still in fp32; phase 2
+// sorts the frozen slices by k_e and launches iteration k over the prefix already switched.
+// =====================================================================================================
+__global__ void k_lexmax_finish(const double2* __restrict__ cand, int stride, int ntiles, SliceStats* stats) {
+    __shared__ double red[64];
+    const int s = blockIdx.x;
+    double re = -INFINITY, im = -INFINITY;
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x) {
+        const double2 c = cand[(long long)s * stride + i];
+        if (c.x > re || (c.x == re && c.y > im)) { re = c.x; im = c.y; }
+    }
+    block_lexmax(re, im, red);
+    if (threadIdx.x == 0) { stats[s].re64_key = f64_ordered(re); stats[s].im64_key = f64_ordered(im); }
+}
+
+__global__ void k_mask_to_c64(const uint8_t* __restrict__ m, Cx<float>* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = cmake<float>(m[i] ? 1.f : 0.f, 0.f);
+}
+
+// ascending sort of every (slice, iteration) segment of the support record: the replay sums in a fixed order
+__global__ void k_sort_segments(const int* __restrict__ list, const int* __restrict__ esc, unsigned* arena, const int* __restrict__ astart,
+                                int acap, int niter) {
+    extern __shared__ unsigned seg_sh[];
+    const int s = list[blockIdx.y], i = blockIdx.x;
+    if (i >= esc[s] - 1) return;
+    const int a0 = astart[(long long)s * (niter + 1) + i], n = astart[(long long)s * (niter + 1) + i + 1] - a0;
+    if (n <= 1) return;
+    int m = 1; while (m < n) m <<= 1;
+    unsigned* seg = arena + (long long)s * acap + a0;
+    for (int t = threadIdx.x; t < m; t += blockDim.x) seg_sh[t] = t < n ? seg[t] : 0xffffffffu;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < m; t += blockDim.x) {
+                const int p = t ^ j;
+                if (p > t) {
+                    const unsigned a = seg_sh[t], b = seg_sh[p];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { seg_sh[t] = b; seg_sh[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int t = threadIdx.x; t < n; t += blockDim.x) seg[t] = seg_sh[t];
+}
+
+// one iteration of the sparse-domain float64 recursion (see the header of this section)
+template <int OP>
+__global__ void __launch_bounds__(128)
+k_replay(const int i, const int* __restrict__ list, const int* __restrict__ esc, const unsigned* __restrict__ arena,
+         const int* __restrict__ astart, double2* __restrict__ yval, const int acap, const int niter,
+         const Cx<double>* __restrict__ X0, const Cx<double>* __restrict__ mhat, const Cx<double>* __restrict__ tau,
+         const long long first_slice, const int spm, const int n1, const int n2, const double alpha, const double inv_n) {
+    __shared__ unsigned sp[128];
+    __shared__ double2 sy[128];
+    const int s = list[blockIdx.y];
+    if (i >= esc[s] - 1) return;
+    const int* as = astart + (long long)s * (niter + 1);
+    const int a0 = as[i], n = as[i + 1] - a0;
+    if ((int)blockIdx.x * 128 >= n) return;
+    const int p0 = i > 0 ? as[i - 1] : 0, np = i > 0 ? a0 - p0 : 0;
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    const bool valid = t < n;
+    const unsigned* ar = arena + (long long)s * acap;
+    double2* yv = yval + (long long)s * acap;
+    const unsigned pj = valid ? ar[a0 + t] : 0u;
+    const int jr = (int)(pj >> 16), jc = (int)(pj & 0xffffu);
+    const long long ne = (long long)n1 * n2;
+    const Cx<double> x0 = valid ? X0[(long long)s * ne + (long long)jr * n2 + jc] : cmake<double>(0.0, 0.0);
+    const Cx<double>* __restrict__ mh = mhat + ((first_slice + s) / spm) * ne;
+    double accx = 0.0, accy = 0.0, selfx = 0.0, selfy = 0.0;
+    for (int q0 = 0; q0 < np; q0 += 128) {
+        const int nq = min(128, np - q0);
+        __syncthreads();
+        if ((int)threadIdx.x < nq) { sp[threadIdx.x] = ar[p0 + q0 + threadIdx.x]; sy[threadIdx.x] = yv[p0 + q0 + threadIdx.x]; }
+        __syncthreads();
+        if (valid) {
+            for (int q = 0; q < nq; ++q) {
+                const unsigned ps = sp[q];
+                const double2 ys = sy[q];
+                if (ps == pj) { selfx = ys.x; selfy = ys.y; }
+                int dr = jr - (int)(ps >> 16); if (dr < 0) dr += n1;
+                int dc = jc - (int)(ps & 0xffffu); if (dc < 0) dc += n2;
+                const double2 m = __ldg(reinterpret_cast<const double2*>(mh) + (long long)dr * n2 + dc);
+                accx += m.x * ys.x - m.y * ys.y;
+                accy += m.x * ys.y + m.y * ys.x;
+            }
+        }
+    }
+    if (!valid) return;
+    Cx<double> X = x0;
+    if (i > 0) X = cmake<double>(alpha * x0.x + selfx - alpha * inv_n * accx, alpha * x0.y + selfy - alpha * inv_n * accy);
+    const Cx<double> tk = tau[(long long)s * niter + i];
+    const double a = tk.x, b = tk.y;
+    const Cx<double> y = apply_threshold<OP, double>(X, a, b, a * a - b * b, 2.0 * a * b);
+    yv[a0 + t] = make_double2(y.x, y.y);
+}
+
+// restart spectrum of a frozen slice: zero, then y_{k_e - 1} at its support
+__global__ void k_zero_slices(const int* __restrict__ list, Cx<double>* W, long long ne) {
+    const int s = list[blockIdx.y];
+    double2* w = reinterpret_cast<double2*>(W + (long long)s * ne);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) w[i] = make_double2(0.0, 0.0);
+}
+__global__ void k_scatter_restart(const int* __restrict__ list, const int* __restrict__ esc, const unsigned* __restrict__ arena,
+                                  const int* __restrict__ astart, const double2* __restrict__ yval, int acap, int niter,
+                                  Cx<double>* W, int n2, long long ne, double* S) {
+    const int s = list[blockIdx.y];
+    const int ke = esc[s] - 1;              // >= 1 for every slice of this list
+    const int a0 = astart[(long long)s * (niter + 1) + ke - 1], n = astart[(long long)s * (niter + 1) + ke] - a0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) S[(long long)s * (niter + 1) + ke] = 0.0;      // sum |x_{k_e - 1}| is recomputed in double
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const unsigned pj = arena[(long long)s * acap + a0 + t];
+        const double2 y = yval[(long long)s * acap + a0 + t];
+        W[(long long)s * ne + (long long)(pj >> 16) * n2 + (pj & 0xffffu)] = cmake<double>(y.x, y.y);
+    }
+}
+
+void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
+    p3d_plan* P = R.P;
+    const p3d_pocs_params& pr = *R.pr;
+    const int niter = pr.niter;
+    const int64_t ne = (int64_t)P->n1 * P->n2;
+    cudaStream_t st = L.stream;
+    const F64Kernels K = f64_kernels(P->f64);
+    const int64_t band_max = 32768;
+    const int acap = L.arena_cap;
+
+    const Cx<float>* D;
+    if (R.x_mem == P3D_MEM_HOST) {
+        P3D_CUDA(cudaMemcpyAsync(L.D, R.x + first * ne, sizeof(Cx<float>) * ne * count, cudaMemcpyHostToDevice, st));
+        D = L.D;
+    } else {
+        D = R.x + first * ne;
+    }
+    Cx<float>* OUT = (R.out_mem == P3D_MEM_HOST || R.schedule_only) ? L.OUT : R.out + first * ne;
+
+    P3D_CUDA(cudaMemsetAsync(L.S, 0, sizeof(double) * count * (niter + 1), st));
+    P3D_CUDA(cudaMemsetAsync(L.stop, 0, sizeof(int) * count, st));
+    P3D_CUDA(cudaMemsetAsync(L.esc, 0, sizeof(int) * count, st));
+    P3D_CUDA(cudaMemsetAsync(L.acnt, 0, sizeof(int) * count, st));
+    P3D_CUDA(cudaMemsetAsync(L.astart, 0, sizeof(int) * count * (niter + 1), st));
+    for (int64_t i = 0; i < count; ++i) {
+        memset(&L.h_stats[i], 0, sizeof(SliceStats));
+        L.h_stats[i].minabs_bits = 0x7f800000u;
+        L.h_stats[i].minabs64_key = ~0ull;
+        L.h_list[i] = (int)i;
+    }
+    P3D_CUDA(cudaMemcpyAsync(L.stats, L.h_stats, sizeof(SliceStats) * count, cudaMemcpyHostToDevice, st));
+    P3D_CUDA(cudaMemcpyAsync(L.list, L.h_list, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+
+    P->geom.slices_per_mask = (int)std::min<int64_t>(R.spm, 0x7fffffff);
+    PocsGeom G64 = K.cfg.geom; G64.slices_per_mask = P->geom.slices_per_mask;
+    GenericCfg cfg64 = K.cfg; cfg64.geom = G64;
+
+    const bool data_driven = pr.thresh_model == P3D_MODEL_DATA_DRIVEN;
+    const bool adaptive = pr.version == P3D_VERSION_ADAPTIVE;
+
+    BandArgs<float> A;
+    memset(&A, 0, sizeof(A));
+    A.mask = R.dmask; A.mbits = R.dmbits; A.niter = niter; A.eps = pr.eps; A.alpha = (float)pr.alpha;
+    A.inv_n = (float)(1.0 / ((double)P->n1 * (double)P->n2));
+    A.W = L.W; A.D = D; A.OUT = OUT; A.first_slice = first; A.tau = L.tau; A.S = L.S; A.stop = L.stop; A.stats = L.stats;
+    A.exact_tie = (pr.thresh_model == P3D_MODEL_INVERSE_PROPORTIONAL || data_driven || pr.decay_factors) ? 1 : 0;
+    A.esc = L.esc;
+
+    BandArgs<double> A64;
+    memset(&A64, 0, sizeof(A64));
+    A64.mask = R.dmask; A64.mbits = R.dmbits64; A64.niter = niter; A64.eps = pr.eps; A64.alpha = pr.alpha;
+    A64.inv_n = 1.0 / ((double)P->n1 * (double)P->n2);
+    A64.W = L.W64; A64.D32 = D; A64.OUT32 = OUT; A64.first_slice = first; A64.tau = L.tau64; A64.S = L.S; A64.stop = L.stop;
+    A64.stats = L.stats; A64.exact_tie = 1; A64.cand = L.cand; A64.cand_stride = L.cand_stride; A64.esc = L.esc;
+
+    // launch helpers over a (compacted) list of slices of this chunk
+    auto rows_init64 = [&](BandArgs<double> B, const int* list, int n) {
+        prof_begin(P, L.events, st, 10);
+        for (int64_t o = 0; o < n; o += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, n - o);
+            B.list = list + o;
+            if (K.spec_rows) K.spec.rows_init_io32(G64, K.tw_rows, B, nb, st);
+            else generic64_rows_init(cfg64, K.a2, B, nb, st);
+        }
+        prof_end(P, L.events, st);
+        P3D_CUDA(cudaGetLastError());
+    };
+    auto cols64 = [&](BandArgs<double> B, const int* list, int n, int op) {
+        prof_begin(P, L.events, st, 8);
+        for (int64_t o = 0; o < n; o += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, n - o);
+            B.list = list + o;
+            if (K.spec_cols) K.spec.cols_iter(G64, K.tw_cols, B, nb, op, st);
+            else generic64_cols_iter(cfg64, K.a1, B, nb, op, st);
+        }
+        prof_end(P, L.events, st);
+        P3D_CUDA(cudaGetLastError());
+    };
+    auto rows64 = [&](BandArgs<double> B, const int* list, int n) {
+        prof_begin(P, L.events, st, 9);
+        for (int64_t o = 0; o < n; o += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, n - o);
+            B.list = list + o;
+            if (K.spec_rows) K.spec.rows_iter_io32(G64, K.tw_rows, B, nb, st);
+            else generic64_rows_iter(cfg64, K.a2, B, nb, st);
+        }
+        prof_end(P, L.events, st);
+        P3D_CUDA(cudaGetLastError());
+    };
+    auto for_list32 = [&](BandArgs<float> B, const int* list, int n, auto&& fn) {
+        for (int64_t o = 0; o < n; o += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, n - o);
+            B.list = list + o;
+            fn(B, nb);
+        }
+    };
+
+    // ---- setup: row FFT of d (fp32 state), statistics of X0 in complex128 (X0 stays in W64 for the replay) -----------
+    {
+        BandArgs<float> B = A;
+        B.adaptive = 0; B.accum = 1; B.store_x0 = data_driven ? 1 : 0;
+        for_list32(B, L.list, (int)count, [&](const BandArgs<float>& b, int nb) {
+            launch_rows_init(P, L, b, nb);
+            if (data_driven) launch_cols_stats(P, L, b, nb);
+        });
+        BandArgs<double> B64 = A64;
+        B64.adaptive = 0; B64.accum = 0; B64.src_out = 0; B64.store_x0_inplace = 1;
+        rows_init64(B64, L.list, (int)count);
+        prof_begin(P, L.events, st, 10);
+        for (int64_t o = 0; o < count; o += band_max) {
+            const int nb = (int)std::min<int64_t>(band_max, count - o);
+            B64.list = L.list + o;
+            if (K.spec_cols) K.spec.cols_stats(G64, K.tw_cols, B64, nb, st);
+            else generic64_cols_stats(cfg64, K.a1, B64, nb, st);
+        }
+        k_lexmax_finish<<<(unsigned)count, 128, 0, st>>>(L.cand, L.cand_stride, K.cand_stride, L.stats);
+        prof_end(P, L.events, st);
+        P3D_CUDA(cudaGetLastError());
+    }
+    P3D_CUDA(cudaMemcpyAsync(L.h_stats, L.stats, sizeof(SliceStats) * count, cudaMemcpyDeviceToHost, st));
+    P3D_CUDA(cudaStreamSynchronize(st));
+
+    // ---- schedule (host, double) ---------------------------------------------------------------------------------
+    std::vector<cd> tau;
+    const double eps32 = 5.9604644775390625e-08;      // 2^-24
+    // adaptive POCS has no sparse recursion of this form: complex128 from the first iteration (an infinite guard band)
+    const double gfac = adaptive ? std::numeric_limits<double>::infinity() : P->guard_factor;
+    auto store_tau = [&](int64_t i) {
+        for (int k = 0; k < niter; ++k) {
+            L.h_tau[i * niter + k] = cmake<float>((float)tau[k].real(), (float)tau[k].imag());
+            L.h_tau64[i * niter + k] = cmake<double>(tau[k].real(), tau[k].imag());
+            if (R.tau_out) { R.tau_out[((first + i) * niter + k) * 2] = tau[k].real(); R.tau_out[((first + i) * niter + k) * 2 + 1] = tau[k].imag(); }
+        }
+    };
+    auto guard_of = [&](const SliceStats& ss) {
+        const double g = gfac * eps32 * std::sqrt(ss.sumsq / (double)std::max<unsigned long long>(1ull, ss.nnz));
+        return (float)std::min(g, 3.0e38);
+    };
+    if (!data_driven) {
+        for (int64_t i = 0; i < count; ++i) {
+            const SliceStats& ss = L.h_stats[i];
+            L.h_stop[i] = ss.nnz == 0 ? -1 : 0;
+            ScheduleStats sc;
+            sc.z = cd(f64_from_ordered(ss.re64_key), f64_from_ordered(ss.im64_key));
+            sc.sumsq = ss.sumsq; sc.vmax = f64_from_ordered(ss.maxabs64_key); sc.vmin = f64_from_ordered(ss.minabs64_key);
+            bool is_real = false;
+            host_schedule(pr, sc, ne, tau, is_real);
+            if (pr.sqrt_decay) apply_sqrt_decay(tau, is_real);
+            store_tau(i);
+            L.h_guard[i] = guard_of(ss);
+        }
+    } else {
+        // thresholds = order statistics of the fp32 X0 (sorted on the device); the complex128 phase uses the same values
+        size_t need = 0;
+        cub::DeviceRadixSort::SortKeysDescending(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (long long)ne, 0, 64, st);
+        if (need > L.cub_temp_bytes) {
+            if (L.cub_temp) cudaFree(L.cub_temp);
+            L.cub_temp = nullptr; L.cub_temp_bytes = 0;
+            P3D_CUDA(cudaMalloc(&L.cub_temp, need)); L.cub_temp_bytes = need;
+        }
+        for (int64_t i = 0; i < count; ++i) {
+            L.h_stop[i] = L.h_stats[i].nnz == 0 ? -1 : 0;
+            if (L.h_stop[i]) continue;
+            cd tmin, tmax;
+            schedule_bounds(pr, stats_f32(L.h_stats[i]), ne, tmin, tmax);
+            const unsigned long long lo = lex_key((float)tmin.real(), (float)tmin.imag());
+            const unsigned long long hi = lex_key((float)tmax.real(), (float)tmax.imag());
+            unsigned long long* keys = reinterpret_cast<unsigned long long*>(OUT + i * ne);
+            unsigned long long* sorted = reinterpret_cast<unsigned long long*>(L.W + i * ne);
+            prof_begin(P, L.events, st, 6);
+            k_make_keys<<<std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(keys, ne, lo, hi, L.stats + i);
+            size_t tb = L.cub_temp_bytes;
+            cub::DeviceRadixSort::SortKeysDescending(L.cub_temp, tb, keys, sorted, (long long)ne, 0, 64, st);
+            k_pick_tau<<<1, 128, 0, st>>>(sorted, L.stats + i, L.tau + i * niter, niter);
+            prof_end(P, L.events, st);
+        }
+        P3D_CUDA(cudaGetLastError());
+        P3D_CUDA(cudaMemcpyAsync(L.h_tau, L.tau, sizeof(Cx<float>) * count * niter, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(L.h_stats, L.stats, sizeof(SliceStats) * count, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < count; ++i) {
+            tau.assign(niter, cd(0, 0));
+            L.h_guard[i] = 0.f;
+            if (!L.h_stop[i]) {
+                P3D_REQUIRE(L.h_stats[i].n_cand > 0, P3D_ERR_NUMERIC,
+                            "data-driven schedule: no coefficient between tau_min and tau_max in slice %lld", (long long)(first + i));
+                for (int k = 0; k < niter; ++k) tau[k] = cd(L.h_tau[i * niter + k].x, L.h_tau[i * niter + k].y);
+                if (pr.sqrt_decay) apply_sqrt_decay(tau, false);
+                L.h_guard[i] = guard_of(L.h_stats[i]);
+            }
+            store_tau(i);
+        }
+    }
+    if (R.schedule_only) { L.pending = false; return; }
+
+    P3D_CUDA(cudaMemcpyAsync(L.tau, L.h_tau, sizeof(Cx<float>) * count * niter, cudaMemcpyHostToDevice, st));
+    P3D_CUDA(cudaMemcpyAsync(L.tau64, L.h_tau64, sizeof(Cx<double>) * count * niter, cudaMemcpyHostToDevice, st));
+    P3D_CUDA(cudaMemcpyAsync(L.stop, L.h_stop, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+    P3D_CUDA(cudaMemcpyAsync(L.guard, L.h_guard, sizeof(float) * count, cudaMemcpyHostToDevice, st));
+    for (int64_t i = 0; i < count; ++i)
+        if (L.h_stop[i] < 0)
+            P3D_CUDA(cudaMemcpyAsync(OUT + i * ne, D + i * ne, sizeof(Cx<float>) * ne, cudaMemcpyDeviceToDevice, st));
+
+    // W was used as sort scratch (data-driven): redo the row pass
+    if (data_driven) {
+        BandArgs<float> B = A;
+        B.adaptive = 0; B.accum = 0;
+        for_list32(B, L.list, (int)count, [&](const BandArgs<float>& b, int nb) { launch_rows_init(P, L, b, nb); });
+    }
+
+    // ---- phase 1: fp32 pilot over the slices still in fp32 -----------------------------------------------------------
+    const bool guard_on = gfac > 0.0;
+    std::vector<int> active;
+    active.reserve((size_t)count);
+    for (int64_t i = 0; i < count; ++i) if (L.h_stop[i] == 0) active.push_back((int)i);
+    auto upload_list = [&](const std::vector<int>& v) {
+        // the previous launches were waited for (or never used the list): the pinned mirror is free
+        memcpy(L.h_list, v.data(), sizeof(int) * v.size());
+        if (!v.empty()) P3D_CUDA(cudaMemcpyAsync(L.list, L.h_list, sizeof(int) * v.size(), cudaMemcpyHostToDevice, st));
+    };
+    upload_list(active);
+    const bool need_sync = guard_on || pr.eps > 0.0;
+    const int seg = std::max(1, P->seg_iters);
+    int k = 0;
+    while (k < niter && !active.empty()) {
+        const int kend = need_sync ? std::min(niter, k + (k == 0 && guard_on ? 1 : seg)) : niter;
+        for (; k < kend; ++k) {
+            BandArgs<float> B = A;
+            B.guard = guard_on ? L.guard : nullptr;
+            if (guard_on) { B.arena = L.arena; B.acnt = L.acnt; B.astart = L.astart; B.arena_cap = acap; }
+            B.k = k; B.last = (k == niter - 1) ? 1 : 0;
+            B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
+            for_list32(B, L.list, (int)active.size(), [&](const BandArgs<float>& b, int nb) {
+                launch_cols_iter(P, L, b, nb, pr.thresh_op);
+                launch_rows_iter(P, L, b, nb);
+            });
+        }
+        if (k < niter && need_sync) {
+            P3D_CUDA(cudaMemcpyAsync(L.h_esc, L.esc, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+            P3D_CUDA(cudaMemcpyAsync(L.h_stop, L.stop, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+            P3D_CUDA(cudaStreamSynchronize(st));
+            size_t w = 0;
+            for (size_t r = 0; r < active.size(); ++r) {
+                const int i = active[r];
+                if (L.h_esc[i] == 0 && L.h_stop[i] == 0) active[w++] = i;
+            }
+            if (w != active.size()) { active.resize(w); upload_list(active); }
+        }
+    }
+
+    // ---- phase 2: exact restart + complex128 iterations of the frozen slices ---------------------------------------
+    if (guard_on) {
+        P3D_CUDA(cudaMemcpyAsync(L.h_esc, L.esc, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(L.h_stop, L.stop, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(L.h_astart, L.astart, sizeof(int) * count * (niter + 1), cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaStreamSynchronize(st));
+        std::vector<std::pair<int, int>> e64;       // (k_e = first complex128 iteration, slice)
+        for (int64_t i = 0; i < count; ++i)
+            if (L.h_esc[i] > 0 && L.h_stop[i] == 0) e64.push_back(std::make_pair(L.h_esc[i] - 1, (int)i));
+        std::sort(e64.begin(), e64.end());
+        if (!e64.empty()) {
+            const int n64 = (int)e64.size();
+            std::vector<int> order((size_t)n64);
+            int n0 = 0;                              // slices frozen in the very first iteration: restart state = d
+            for (int r = 0; r < n64; ++r) { order[r] = e64[r].second; if (e64[r].first == 0) ++n0; }
+            upload_list(order);
+            const int n1r = n64 - n0;                // slices with a replay
+            const int* list1 = L.list + n0;
+            if (n0 > 0) {
+                BandArgs<double> B64 = A64;
+                B64.src_out = 0; B64.adaptive = adaptive ? 1 : 0; B64.accum = 0;
+                rows_init64(B64, L.list, n0);
+            }
+            if (n1r > 0) {
+                prof_begin(P, L.events, st, 11);
+                const int kmax = e64.back().first;                       // replay iterations 0 .. kmax - 1
+                // largest support per replay iteration (over the slices that need it) sizes the launches
+                std::vector<int> smax((size_t)kmax, 0);
+                int seg_max = 0;
+                for (int r = n0; r < n64; ++r) {
+                    const int* as = L.h_astart + (int64_t)e64[r].second * (niter + 1);
+                    for (int i = 0; i < e64[r].first; ++i) { smax[i] = std::max(smax[i], as[i + 1] - as[i]); seg_max = std::max(seg_max, as[i + 1] - as[i]); }
+                }
+                int pow2 = 1; while (pow2 < seg_max) pow2 <<= 1;
+                static bool sort_cfg = false;
+                if (!sort_cfg) { cudaFuncSetAttribute(k_sort_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4); sort_cfg = true; }
+                for (int64_t o = 0; o < n1r; o += band_max) {
+                    const int nb = (int)std::min<int64_t>(band_max, n1r - o);
+                    k_sort_segments<<<dim3((unsigned)kmax, (unsigned)nb), 256, sizeof(unsigned) * pow2, st>>>(list1 + o, L.esc, L.arena, L.astart, acap, niter);
+                }
+                for (int i = 0; i < kmax; ++i) {
+                    if (smax[i] == 0) continue;
+                    const unsigned gx = (unsigned)((smax[i] + 127) / 128);
+                    for (int64_t o = 0; o < n1r; o += band_max) {
+                        const int nb = (int)std::min<int64_t>(band_max, n1r - o);
+                        const dim3 grid(gx, (unsigned)nb);
+#define P3D_REPLAY(OPV) k_replay<OPV><<<grid, 128, 0, st>>>(i, list1 + o, L.esc, L.arena, L.astart, L.yval, acap, niter, L.W64, P->mhat, L.tau64, \
+                                                            (long long)first, (int)std::min<int64_t>(R.spm, 0x7fffffff), P->n1, P->n2, pr.alpha, A64.inv_n)
+                        if (pr.thresh_op == P3D_OP_HARD) P3D_REPLAY(P3D_OP_HARD);
+                        else if (pr.thresh_op == P3D_OP_SOFT) P3D_REPLAY(P3D_OP_SOFT);
+                        else P3D_REPLAY(P3D_OP_GARROTE);
+#undef P3D_REPLAY
+                    }
+                }
+                for (int64_t o = 0; o < n1r; o += band_max) {
+                    const int nb = (int)std::min<int64_t>(band_max, n1r - o);
+                    k_zero_slices<<<dim3((unsigned)std::min<long long>((ne + 255) / 256, 592), (unsigned)nb), 256, 0, st>>>(list1 + o, L.W64, ne);
+                    k_scatter_restart<<<dim3((unsigned)std::max(1, (seg_max + 255) / 256), (unsigned)nb), 256, 0, st>>>(list1 + o, L.esc, L.arena, L.astart, L.yval, acap, niter,
+                                                                                                                     L.W64, P->n2, ne, L.S);
+                }
+                prof_end(P, L.events, st);
+                P3D_CUDA(cudaGetLastError());
+                // inverse column pass + row pass of iteration k_e - 1 in complex128: x_{k_e - 1} and its row FFT
+                BandArgs<double> B64 = A64;
+                B64.restart = 1; B64.k = 0; B64.last = 0; B64.write_out = 0;
+                cols64(B64, list1, n1r, P3D_OP_RESTART);
+                rows64(B64, list1, n1r);
+            }
+            BandArgs<double> B64 = A64;
+            int ptr = 0;
+            int64_t its = 0;
+            for (int kk = e64[0].first; kk < niter; ++kk) {
+                while (ptr < n64 && e64[ptr].first <= kk) ++ptr;
+                B64.k = kk; B64.last = (kk == niter - 1) ? 1 : 0;
+                B64.write_out = (B64.last || (pr.eps > 0.0 && kk >= 3)) ? 1 : 0;
+                cols64(B64, L.list, ptr, pr.thresh_op);
+                rows64(B64, L.list, ptr);
+                its += ptr;
+            }
+            L.n_escalated += n64; L.n_esc_iters += its;
+        }
+    }
+
+    // ---- results ------------------------------------------------------------------------------------
+    if (R.out_mem == P3D_MEM_HOST)
+        P3D_CUDA(cudaMemcpyAsync(R.out + first * ne, OUT, sizeof(Cx<float>) * ne * count, cudaMemcpyDeviceToHost, st));
+    P3D_CUDA(cudaMemcpyAsync(L.h_S, L.S, sizeof(double) * count * (niter + 1), cudaMemcpyDeviceToHost, st));
+    P3D_CUDA(cudaMemcpyAsync(L.h_stop, L.stop, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+    L.pending = true; L.p_first = first; L.p_count = count;
+}
+
+// fft2 of the mask planes in complex128 (the kernel of the sparse recursion), once per run
+void compute_mhat(p3d_plan* P, const uint8_t* dmask, int64_t n_masks, cudaStream_t st) {
+    const int64_t ne = (int64_t)P->n1 * P->n2;
+    const F64Kernels K = f64_kernels(P->f64);
+    if (n_masks > P->mhat_masks || K.cand_stride > P->mh_cand_stride) {
+        for (void* p : {(void*)P->mhat, (void*)P->mask_c64, (void*)P->mh_stats, (void*)P->mh_cand}) if (p) cudaFree(p);
+        P->mhat = nullptr; P->mask_c64 = nullptr; P->mh_stats = nullptr; P->mh_cand = nullptr; P->mhat_masks = 0;
+        P3D_CUDA(cudaMalloc(&P->mhat, sizeof(Cx<double>) * ne * n_masks));
+        P3D_CUDA(cudaMalloc(&P->mask_c64, sizeof(Cx<float>) * ne * n_masks));
+        P3D_CUDA(cudaMalloc(&P->mh_stats, sizeof(SliceStats) * n_masks));
+        P3D_CUDA(cudaMalloc(&P->mh_cand, sizeof(double2) * n_masks * K.cand_stride));
+        P->mhat_masks = n_masks; P->mh_cand_stride = K.cand_stride;
+    }
+    k_mask_to_c64<<<(unsigned)std::min<long long>((ne * n_masks + 255) / 256, 148 * 16), 256, 0, st>>>(dmask, P->mask_c64, ne * n_masks);
+    PocsGeom G64 = K.cfg.geom; G64.slices_per_mask = 1;
+    GenericCfg cfg64 = K.cfg; cfg64.geom = G64;
+    BandArgs<double> M;
+    memset(&M, 0, sizeof(M));
+    M.W = P->mhat; M.D32 = P->mask_c64; M.OUT32 = P->mask_c64; M.mask = dmask; M.niter = 1; M.stats = P->mh_stats;
+    M.cand = P->mh_cand; M.cand_stride = P->mh_cand_stride; M.store_x0_inplace = 1; M.alpha = 1.0; M.inv_n = 1.0;
+    for (int64_t o = 0; o < n_masks; o += 32768) {
+        const int nb = (int)std::min<int64_t>(32768, n_masks - o);
+        BandArgs<double> B = M;
+        B.W += o * ne; B.D32 += o * ne; B.OUT32 += o * ne; B.stats += o; B.cand += o * M.cand_stride; B.first_slice = o;
+        if (K.spec_rows) K.spec.rows_init_io32(G64, K.tw_rows, B, nb, st); else generic64_rows_init(cfg64, K.a2, B, nb, st);
+        if (K.spec_cols) K.spec.cols_stats(G64, K.tw_cols, B, nb, st); else generic64_cols_stats(cfg64, K.a1, B, nb, st);
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaStreamSynchronize(st));
 }
 
 int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, const uint8_t* mask,
@@ -602,6 +1190,12 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     }
     if (n_slices == 0) return P3D_OK;
     if (spm <= 0) spm = n_slices;
+    if (!schedule_only && x_mem == P3D_MEM_DEVICE && out_mem == P3D_MEM_DEVICE) {
+        // the observed slices are read in place in every iteration while results (and scratch) go to `out`
+        const char* xa = (const char*)x; const char* oa = (const char*)out;
+        const size_t nb = sizeof(Cx<float>) * (size_t)P->n1 * P->n2 * (size_t)n_slices;
+        P3D_REQUIRE(xa + nb <= oa || oa + nb <= xa, P3D_ERR_BAD_ARG, "device buffers x and out must not overlap");
+    }
     DeviceGuard guard(P->device);
 
     if (P->precision == 64 && !filt) {
@@ -618,21 +1212,28 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
                        cost_out, costs_out, tau_out, schedule_only, P->max_slices);
     }
     const bool host_in = x_mem == P3D_MEM_HOST, host_out = (out_mem == P3D_MEM_HOST) || schedule_only;
-    // host data: four lanes (streams + buffer sets) rotate, so that the D2H of chunk i and the H2D of chunk
-    // i+4 hide behind the iterations of chunks i+1..i+3 even when the PCIe path is slow (8 ranks sharing
+    // escalating precision: every ordinary POCS run unless the plan was pinned to fp32 (the percentile operators and the
+    // kx-ky filter mode have no threshold decision that fp32 could get wrong / run in fp32 only)
+    const bool escalate = P->precision == 0 && !filt && !pr->thresh_percentile;
+    // host data: four lanes (streams + buffer sets), each fed by its own host thread, so that the D2H of chunk i and the
+    // H2D of chunk i+4 hide behind the iterations of chunks i+1..i+3 even when the PCIe path is slow (8 ranks sharing
     // one host: 8-11 GB/s per direction measured; e2e at 8 GPUs 444k -> 506k slice-it/s going from 2 to 4
     // lanes, 76.6k -> 80.9k on one GPU); device-resident data need one lane.
     // (the percentile operators share one scratch area and sort inside the iteration loop: one lane)
     const int lanes = pr->thresh_percentile ? 1 : (P->n_lanes > 0 ? P->n_lanes : ((host_in || host_out) ? 4 : 1));
     if ((int)P->lanes.size() < lanes) P->lanes.resize(lanes);
-    const int nbuf = 1 + (host_in ? 1 : 0) + (host_out ? 1 : 0);
-    for (auto& L : P->lanes) L.pending = false;
-    // chunk size: everything at once on one lane; with two lanes at least two chunks per lane
+    const int nbuf = 1 + (host_in ? 1 : 0) + (host_out ? 1 : 0) + (escalate ? 2 : 0);
+    for (auto& L : P->lanes) { L.pending = false; L.n_escalated = 0; L.n_esc_iters = 0; }
+    int cand_stride = 0;
+    if (escalate) {
+        if (!P->f64) { P->f64 = f64_create(P->device, P->n1, P->n2, &P->ax1, &P->ax2, P->smem_optin); f64_install_spec(P->f64, P->spec_variant64); }
+        f64_set_force_generic(P->f64, P->force_generic ? 1 : 0);
+        cand_stride = f64_kernels(P->f64).cand_stride;
+    }
+    // chunk size: everything at once on one lane; with several lanes at least two chunks per lane
     // (copy/compute overlap) but never tiny chunks
     int64_t want = n_slices;
     if (lanes > 1) {
-        // ~4 chunks per lane keep the un-overlapped first H2D / last D2H short; chunks stay large
-        // enough (>= ~48 MB of slices) to fill the GPU
         const int64_t ne_ = (int64_t)P->n1 * P->n2;
         const int64_t min_chunk = std::max<int64_t>(1, std::min<int64_t>(n_slices, (int64_t)(48e6 / (8.0 * (double)ne_)) + 1));
         // full-size chunks: ~2 per lane; the first and last chunks of a call are shorter (ramp below), so the
@@ -648,17 +1249,21 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
         for (auto& L : P->lanes) { cudaStream_t st = L.stream; L.stream = nullptr; free_lane(L); L.stream = st; }
         cap = auto_capacity(P, want, nbuf, lanes);
     }
-    for (int i = 0; i < lanes; ++i) ensure_lane(P, P->lanes[i], cap, pr->niter, host_in, host_out);
+    for (int i = 0; i < lanes; ++i) ensure_lane(P, P->lanes[i], cap, pr->niter, host_in, host_out, escalate, cand_stride);
 
     RunCtx R;
     R.P = P; R.pr = pr; R.x = (const Cx<float>*)x; R.x_mem = x_mem; R.spm = spm;
     R.out = (Cx<float>*)out; R.out_mem = out_mem; R.niter_out = niter_out; R.cost_out = cost_out;
     R.costs_out = costs_out; R.tau_out = tau_out; R.schedule_only = schedule_only;
-    R.dmask = nullptr; R.dmbits = nullptr; R.filt = filt;
+    R.dmask = nullptr; R.dmbits = nullptr; R.filt = filt; R.escalate = escalate;
     if (!schedule_only) {
         const int64_t n_masks = (n_slices + spm - 1) / spm;
         ensure_mask(P, mask, n_masks * (int64_t)P->n1 * P->n2, x_mem, P->lanes[0].stream, &R.dmask);
         R.dmbits = pack_mask(P, R.dmask, n_masks, P->lanes[0].stream);
+        if (escalate) {
+            R.dmbits64 = f64_pack_mask(P->f64, R.dmask, n_masks, P->lanes[0].stream);
+            compute_mhat(P, R.dmask, n_masks, P->lanes[0].stream);
+        }
     }
 
     // chunk sizes: cap/4, cap/2, cap, ..., cap, cap/2, cap/4 (host data on several lanes), else cap
@@ -672,17 +1277,42 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     } else {
         for (int64_t first = 0; first < n_slices; first += cap) sizes.push_back(std::min<int64_t>(cap, n_slices - first));
     }
-    int li = 0;
-    int64_t first = 0;
-    for (const int64_t count : sizes) {
-        Lane& L = P->lanes[li];
-        collect_lane(R, L);
-        process_chunk(R, L, first, count);
-        first += count;
-        li = (li + 1) % lanes;
+    std::vector<int64_t> firsts(sizes.size());
+    { int64_t f = 0; for (size_t i = 0; i < sizes.size(); ++i) { firsts[i] = f; f += sizes[i]; } }
+
+    // one feeder thread per lane: chunk c runs on lane c % lanes; a lane's waits (statistics read-back, list compaction)
+    // never hold up the enqueueing of the other lanes
+    std::vector<int> codes((size_t)lanes, P3D_OK);
+    std::vector<std::string> msgs((size_t)lanes);
+    auto feed = [&](int li) {
+        try {
+            cudaSetDevice(P->device);
+            Lane& L = P->lanes[li];
+            for (size_t c = (size_t)li; c < sizes.size(); c += (size_t)lanes) {
+                collect_lane(R, L);
+                if (escalate) process_chunk_esc(R, L, firsts[c], sizes[c]);
+                else process_chunk(R, L, firsts[c], sizes[c]);
+            }
+            collect_lane(R, L);
+            P3D_CUDA(cudaStreamSynchronize(L.stream));
+        } catch (const P3dFail& f) { codes[li] = f.code; msgs[li] = get_error(); }
+        catch (const std::exception& e) { codes[li] = P3D_ERR_CUDA; msgs[li] = e.what(); }
+    };
+    if (lanes == 1) feed(0);
+    else {
+        std::vector<std::thread> th;
+        for (int li = 0; li < lanes; ++li) th.emplace_back(feed, li);
+        for (auto& t : th) t.join();
     }
-    for (int i = 0; i < lanes; ++i) collect_lane(R, P->lanes[i]);
-    for (int i = 0; i < lanes; ++i) P3D_CUDA(cudaStreamSynchronize(P->lanes[i].stream));
+    for (int li = 0; li < lanes; ++li)
+        if (codes[li] != P3D_OK) {
+            for (int i = 0; i < lanes; ++i) { if (P->lanes[i].stream) cudaStreamSynchronize(P->lanes[i].stream); P->lanes[i].pending = false; }
+            prof_collect(P);
+            set_error("%s", msgs[li].c_str());
+            throw P3dFail{codes[li]};
+        }
+    P->n_escalated = 0; P->n_esc_iters = 0;
+    for (int li = 0; li < lanes; ++li) { P->n_escalated += P->lanes[li].n_escalated; P->n_esc_iters += P->lanes[li].n_esc_iters; }
     prof_collect(P);
     return P3D_OK;
 }
@@ -743,6 +1373,10 @@ int p3d_plan_destroy(p3d_plan* P) {
     if (P->pct_scr) cudaFree(P->pct_scr);
     if (P->pct_keys) cudaFree(P->pct_keys);
     if (P->pct_sorted) cudaFree(P->pct_sorted);
+    if (P->mhat) cudaFree(P->mhat);
+    if (P->mask_c64) cudaFree(P->mask_c64);
+    if (P->mh_stats) cudaFree(P->mh_stats);
+    if (P->mh_cand) cudaFree(P->mh_cand);
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
     delete P;
     return P3D_OK;
@@ -808,9 +1442,9 @@ int p3d_fft2(p3d_plan* P, const void* x, int x_mem, void* out, int out_mem, int6
     if (out_mem == P3D_MEM_HOST) P3D_CUDA(cudaMalloc(&dout, bytes)); else dout = (Cx<float>*)out;
     for (int64_t b0 = 0; b0 < n_slices; b0 += 32768) {
         const int nb = (int)std::min<int64_t>(32768, n_slices - b0);
-        prof_begin(P, st, 7);
+        prof_begin(P, P->events, st, 7);
         generic_fft2(generic_cfg(P), P->ax1.dev(), P->ax2.dev(), din + b0 * ne, dout + b0 * ne, nb, inverse, st);
-        prof_end(P, st);
+        prof_end(P, P->events, st);
     }
     P3D_CUDA(cudaGetLastError());
     P3D_CUDA(cudaDeviceSynchronize());
@@ -854,6 +1488,13 @@ int p3d_plan_event_elapsed_ms(p3d_plan* P, int a, int b, double* ms) {
     P3D_CATCH
 }
 
+int p3d_plan_get_escalation(p3d_plan* P, int64_t* n_slices, int64_t* n_slice_iterations) {
+    if (!P) return P3D_ERR_BAD_ARG;
+    if (n_slices) *n_slices = P->n_escalated;
+    if (n_slice_iterations) *n_slice_iterations = P->n_esc_iters;
+    return P3D_OK;
+}
+
 int p3d_plan_describe(p3d_plan* P, char* buf, int64_t buflen) {
     if (!P || !buf || buflen <= 0) return P3D_ERR_BAD_ARG;
     std::string s = "iline axis: " + P->ax1.describe() + "; xline axis: " + P->ax2.describe();
@@ -862,8 +1503,8 @@ int p3d_plan_describe(p3d_plan* P, char* buf, int64_t buflen) {
          " thr, smem " + std::to_string(P->row_smem) + " B";
     s += std::string("; cols_iter=") + ((P->spec.cols_iter && !P->force_generic) ? P->spec.cols_name : "generic");
     s += std::string("; rows_iter=") + ((P->spec.rows_iter && !P->force_generic) ? P->spec.rows_name : "generic");
-    s += "; precision=" + std::to_string(P->precision);
-    if (P->precision == 64) {
+    s += "; precision=" + (P->precision == 0 ? std::string("escalating(fp32->complex128, guard ") + std::to_string((long long)P->guard_factor) + ")" : std::to_string(P->precision));
+    if (P->precision != 32) {
         const SpecKernels64 k64 = select_spec_kernels64(P->n1, P->n2, P->spec_variant64);
         s += std::string("; cols_iter64=") + ((k64.cols_iter && !P->force_generic) ? k64.cols_name : "generic64");
         s += std::string("; rows_iter64=") + ((k64.rows_iter && !P->force_generic) ? k64.rows_name : "generic64");
@@ -879,9 +1520,12 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     else if (!strcmp(key, "force_generic")) P->force_generic = value != 0;
     else if (!strcmp(key, "lanes")) P->n_lanes = (int)value;
     else if (!strcmp(key, "precision")) {
-        if (value != 32 && value != 64) { set_error("precision must be 32 or 64"); return P3D_ERR_BAD_ARG; }
+        if (value != 0 && value != 32 && value != 64) { set_error("precision must be 0 (escalating), 32 or 64"); return P3D_ERR_BAD_ARG; }
         P->precision = (int)value;
     }
+    else if (!strcmp(key, "guard_factor")) P->guard_factor = (double)value;
+    else if (!strcmp(key, "seg_iters")) P->seg_iters = (int)std::max<int64_t>(1, value);
+    else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(128, value));
     else if (!strcmp(key, "spec_variant")) {
         try { DeviceGuard g(P->device); install_spec(P, (int)value); } catch (const P3dFail& f) { return f.code; }
     }

@@ -94,6 +94,32 @@ void f64_destroy(F64Runner* R) {
     delete R;
 }
 
+F64Kernels f64_kernels(F64Runner* R) {
+    F64Kernels K;
+    K.cfg = R->cfg; K.a1 = R->ax1->dev64(); K.a2 = R->ax2->dev64(); K.spec = R->spec;
+    K.tw_cols = R->tw_cols; K.tw_rows = R->tw_rows;
+    K.spec_cols = R->spec.cols_iter && R->spec.cols_stats && !R->force_generic;
+    K.spec_rows = R->spec.rows_iter_io32 && R->spec.rows_init_io32 && !R->force_generic;
+    const int C = K.spec_cols ? R->spec.cols_C : R->cfg.geom.C;
+    K.cand_stride = (R->n2 + C - 1) / C;
+    return K;
+}
+
+const uint32_t* f64_pack_mask(F64Runner* R, const uint8_t* dmask, int64_t n_masks, cudaStream_t st) {
+    if (!R->spec.pack_mask || R->force_generic) return nullptr;
+    const int64_t words = n_masks * (int64_t)R->n1 * R->spec.rows_T;
+    if (words > R->mbits_words || !R->mbits) {
+        if (R->mbits) cudaFree(R->mbits);
+        R->mbits = nullptr; R->mbits_words = 0;
+        P3D_CUDA(cudaMalloc(&R->mbits, sizeof(uint32_t) * words));
+        R->mbits_words = words;
+    }
+    R->spec.pack_mask(dmask, R->mbits, (int)n_masks, R->n1, st);
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaStreamSynchronize(st));
+    return R->mbits;
+}
+
 static void f64_ensure(F64Runner* R, int64_t n_slices, int niter, int64_t max_slices) {
     const int64_t ne = (int64_t)R->n1 * R->n2;
     int64_t want = n_slices;

@@ -1,6 +1,8 @@
 // Float64 state mode runner (p3d_pocs_f64.cu).
 #pragma once
 #include "p3d_host.h"
+#include "p3d_pocs_launch.h"
+#include "p3d_pocs_spec.cuh"
 
 namespace p3d {
 
@@ -15,5 +17,19 @@ const char* f64_rows_name(const F64Runner* R);
 int f64_run(F64Runner* R, const p3d_pocs_params* pr, const Cx<float>* x, int x_mem, const uint8_t* dmask, int64_t spm,
             Cx<float>* out, int out_mem, int64_t n_slices, int32_t* niter_out, double* cost_out, double* costs_out,
             double* tau_out, bool schedule_only, int64_t max_slices);
+
+
+// ---- complex128 kernels for the escalating-precision engine (p3d_pocs.cu): the runner owns tile geometry, tables,
+// register plans and the packed mask of its row kernel; the engine owns the state buffers
+struct F64Kernels {
+    GenericCfg cfg;
+    AxisDev<double> a1, a2;
+    SpecKernels64 spec;
+    const Cx<double>* tw_cols; const Cx<double>* tw_rows;
+    bool spec_cols, spec_rows;
+    int cand_stride;             // per-CTA lexicographic maxima per slice written by the statistics kernel
+};
+F64Kernels f64_kernels(F64Runner* R);
+const uint32_t* f64_pack_mask(F64Runner* R, const uint8_t* dmask, int64_t n_masks, cudaStream_t st);
 
 }  // namespace p3d

@@ -23,6 +23,7 @@ cudaError_t generic64_configure(const GenericCfg& cfg) {
     P3D_SET((k_cols_generic<double, 1, P3D_OP_HARD>));
     P3D_SET((k_cols_generic<double, 1, P3D_OP_SOFT>));
     P3D_SET((k_cols_generic<double, 1, P3D_OP_GARROTE>));
+    P3D_SET((k_cols_generic<double, 1, P3D_OP_RESTART>));
     P3D_SET((k_rows_generic<double, 0>));
     P3D_SET((k_rows_generic<double, 1>));
 #undef P3D_SET
@@ -42,6 +43,7 @@ void generic64_cols_iter(const GenericCfg& c, const AxisDev<double>& ax1, const 
     switch (op) {
         case P3D_OP_HARD: k_cols_generic<double, 1, P3D_OP_HARD><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
         case P3D_OP_SOFT: k_cols_generic<double, 1, P3D_OP_SOFT><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
+        case P3D_OP_RESTART: k_cols_generic<double, 1, P3D_OP_RESTART><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
         default:          k_cols_generic<double, 1, P3D_OP_GARROTE><<<col_grid(c, ns), c.col_threads, c.col_smem, st>>>(c.geom, ax1, A); break;
     }
 }

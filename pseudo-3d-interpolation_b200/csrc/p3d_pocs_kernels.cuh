@@ -89,7 +89,120 @@ template <typename T> struct BandArgs {
     int write_out, last, adaptive, store_x0, accum;
     int exact_tie;               // thresholds derived from |X0| values (inverse-proportional): honour exact ties
     const float* filt;           // kx-ky filter mode (P3D_OP_FILTER): real (n1, n2) plane multiplied into the spectrum
+    // ---- escalating precision ("precision" = auto) ----
+    const int* list;             // optional: blockIdx.y -> slice index inside the band arrays (compacted launches)
+    int* esc;                    // optional [band]: 0 = fp32 state, k+1 = a coefficient came within `guard` of Re(tau_k)
+                                 // in iteration k: x_k is the last fp32 iterate, complex128 state from k+1 on
+    const float* guard;          // optional [band]: half-width of that guard band (fp32 kernels only)
+    const Cx<float>* D32;        // complex128 kernels with complex64 observed data / results (no converted copies)
+    Cx<float>* OUT32;
+    int src_out;                 // init kernels: source is OUT32 (the fp32 iterate handed over) instead of D32
+    double2* cand;               // complex128 statistics: per-CTA lexicographic maxima [band][cand_stride]
+    int cand_stride;
+    // support record of the fp32 pilot (exact restart): packed (row << 16 | col) of every coefficient kept in iteration k
+    unsigned* arena;             // optional [band][arena_cap]
+    int* acnt;                   // [band] entries used
+    int* astart;                 // [band][niter + 1] first entry of iteration k (astart[.][0] = 0)
+    int arena_cap;
+    int restart;                 // complex128 kernels: this launch rebuilds x_{k_e - 1} (iteration index = esc[s] - 2 per slice)
+    int store_x0_inplace;        // complex128 statistics kernel: leave X0 in W
 };
+
+// internal operator of the complex128 column kernel: the tile already holds a thresholded spectrum (exact restart):
+// inverse transform only
+#define P3D_OP_RESTART 4
+
+// slice handled by this CTA (compacted launches go through the list)
+template <typename T> __device__ __forceinline__ int band_slice(const BandArgs<T>& A) {
+    return A.list ? A.list[blockIdx.y] : (int)blockIdx.y;
+}
+// fp32 kernels: the slice left the fp32 path in an EARLIER iteration (the column pass in which the hit happens is
+// finished by all of its CTAs; the row pass of that iteration is already skipped: see slice_frozen)
+template <typename T> __device__ __forceinline__ bool slice_escalated(const BandArgs<T>& A, const int s) {
+    if (sizeof(T) != 4 || !A.esc) return false;
+    const int e = A.esc[s];
+    return e != 0 && e <= A.k;
+}
+// fp32 row kernels: esc = k + 1 was set by the column pass of this iteration k (or earlier): complex128 redoes iteration k
+template <typename T> __device__ __forceinline__ bool slice_frozen(const BandArgs<T>& A, const int s) {
+    if (sizeof(T) != 4 || !A.esc) return false;
+    const int e = A.esc[s];
+    return e != 0 && e <= A.k + 1;
+}
+
+// Append the packed indices of the coefficients this CTA kept to the slice's support record.  kept: bit e <-> idx[e].
+// sh: >= 34 ints of shared memory.  Every thread of the CTA must call this (barriers inside).
+template <int E>
+__device__ __forceinline__ void record_support(const BandArgs<float>& A, const int s, const unsigned (&idx)[E], const unsigned kept, int* sh) {
+    if (!__syncthreads_or(kept != 0u)) return;
+    const int cnt = __popc(kept);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31 || threadIdx.x == blockDim.x - 1) sh[w] = incl;      // (the last warp of a CTA may be partial)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int i = 0; i < nw; ++i) { const int t = sh[i]; sh[i] = tot; tot += t; }
+        sh[32] = atomicAdd(&A.acnt[s], tot);
+        sh[33] = tot;
+    }
+    __syncthreads();
+    const int base = sh[32], tot = sh[33];
+    if (base + tot > A.arena_cap) {
+        // record full: the support has outgrown the sparse replay -> complex128 takes over from this iteration
+        if (threadIdx.x == 0) A.esc[s] = A.k + 1;
+        return;
+    }
+    unsigned* dst = A.arena + (long long)s * A.arena_cap + base + sh[w] + incl - cnt;
+    int o = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if ((kept >> e) & 1u) dst[o++] = idx[e];
+}
+// Guard band of the escalating-precision mode: |X| within g of Re(tau_k) means that the decision of this or of a
+// later iteration may depend on fp32 rounding.  Tested on |X|^2 (two compares per coefficient).
+template <typename T> struct GuardBand {
+    T lo2, hi2;
+    bool on, hit;
+    // centre = the modulus at which the operator jumps: Re(tau) for hard and soft, sqrt(Re(tau^2)) for garrote
+    __device__ __forceinline__ GuardBand(const BandArgs<T>& A, const int s, const T a, const T b, const int op) {
+        on = (sizeof(T) == 4) && (A.guard != nullptr);
+        hit = false; lo2 = T(-1); hi2 = T(-1);
+        if (on) {
+            const T g = (T)A.guard[s];
+            T c = a;
+            if (op == P3D_OP_GARROTE) { const T c2 = a * a - b * b; c = c2 > T(0) ? sqrt(c2) : T(0); }
+            const T lo = c - g, hi = c + g;
+            if (hi > T(0)) { hi2 = hi * hi; lo2 = lo > T(0) ? lo * lo : T(-1); }
+        }
+    }
+    __device__ __forceinline__ void test(const Cx<T> v) {
+        const T r2 = v.x * v.x + v.y * v.y;
+        hit |= (r2 > lo2) && (r2 < hi2);
+    }
+    __device__ __forceinline__ void commit(const BandArgs<T>& A, const int s) const {
+        if (on && hit) A.esc[s] = A.k + 1;       // every writer of this launch stores the same value
+    }
+};
+
+// lexicographic (re, im) maximum over a CTA; result valid in thread 0.  red: >= 64 doubles of shared memory
+__device__ __forceinline__ void block_lexmax(double& re, double& im, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double r2 = __shfl_xor_sync(0xffffffffu, re, o), i2 = __shfl_xor_sync(0xffffffffu, im, o);
+        if (r2 > re || (r2 == re && i2 > im)) { re = r2; im = i2; }
+    }
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) { red[2 * w] = re; red[2 * w + 1] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < nw; ++i) {
+            const double r2 = red[2 * i], i2 = red[2 * i + 1];
+            if (r2 > re || (r2 == re && i2 > im)) { re = r2; im = i2; }
+        }
+    }
+}
 
 // internal "threshold operator": multiply the spectrum by a real filter plane instead of thresholding
 // (cube_postprocessing_3D.py:254,342  ifft2(filter * fft2(slice)))
@@ -183,9 +296,9 @@ template <typename T, int MODE, int OP>
 __global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_constant__ AxisDev<T> ax1,
                                const __grid_constant__ BandArgs<T> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int s = blockIdx.y;
+    const int s = band_slice(A);
     const int tid = threadIdx.x, nth = blockDim.x;
-    if (MODE == 1) { if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) return; }
+    if (MODE == 1) { if ((!A.restart && slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) || slice_escalated(A, s)) return; }
 
     const int c0 = blockIdx.x * G.C;
     const int nc = min(G.C, G.n2 - c0);
@@ -201,6 +314,15 @@ __global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_
     }
     __syncthreads();
     TileGeom tg; tg.nlines = nc; tg.line_stride = 1; tg.elem_stride = G.C; tg.line_fastest = 1;
+    if (MODE == 1 && OP == P3D_OP_RESTART) {
+        // exact restart: the tile holds the thresholded spectrum already, inverse transform only
+        Cx<T>* Y = line_fft<+1, T>(bufA, bufB, tg, ax1, tid, nth);
+        for (int w = tid; w < tot; w += nth) {
+            const int i = w / nc, c = w - i * nc;
+            Ws[(long long)i * G.n2 + c0 + c] = Y[i * G.C + c];
+        }
+        return;
+    }
     Cx<T>* X = line_fft<-1, T>(bufA, bufB, tg, ax1, tid, nth);
     Cx<T>* other = (X == bufA) ? bufB : bufA;
 
@@ -249,6 +371,24 @@ __global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_
                 atomicMin(&A.stats[s].minabs64_key, ik);
                 atomicAdd(&A.stats[s].sumsq, ss64);
             }
+            if (A.store_x0_inplace) {
+                for (int w = tid; w < tot; w += nth) {
+                    const int i = w / nc, c = w - i * nc;
+                    Ws[(long long)i * G.n2 + c0 + c] = X[i * G.C + c];
+                }
+            }
+            if (A.cand) {
+                // lexicographic maximum of this tile (escalating mode: no stored X0, no second pass)
+                double bre = -INFINITY, bim = -INFINITY;
+                for (int w = tid; w < tot; w += nth) {
+                    const int i = w / nc, c = w - i * nc;
+                    const Cx<T> v = X[i * G.C + c];
+                    if ((double)v.x > bre || ((double)v.x == bre && (double)v.y > bim)) { bre = (double)v.x; bim = (double)v.y; }
+                }
+                __syncthreads();
+                block_lexmax(bre, bim, reinterpret_cast<double*>(other));
+                if (tid == 0) A.cand[(long long)s * A.cand_stride + blockIdx.x] = make_double2(bre, bim);
+            }
         }
         return;
     }
@@ -257,11 +397,33 @@ __global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_
     const Cx<T> tau = A.tau[(long long)s * A.niter + A.k];
     const T a = tau.x, b = tau.y;
     const T t2re = a * a - b * b, t2im = T(2) * a * b;
+    GuardBand<T> gb(A, s, a, b, OP);
     for (int w = tid; w < tot; w += nth) {
         const int i = w / nc, c = w - i * nc;
         Cx<T>* p = X + i * G.C + c;
         if (OP == P3D_OP_FILTER) { const T h = (T)A.filt[(long long)i * G.n2 + c0 + c]; *p = cmake<T>(p->x * h, p->y * h); }
-        else *p = apply_threshold<OP, T>(*p, a, b, t2re, t2im);
+        else { if (sizeof(T) == 4) gb.test(*p); *p = apply_threshold<OP, T>(*p, a, b, t2re, t2im); }
+    }
+    gb.commit(A, s);
+    if (sizeof(T) == 4 && OP != P3D_OP_FILTER && A.arena) {
+        // support record of this tile, 32 coefficients per thread and round (fp32 pilot of the escalating mode)
+        __shared__ int rec_sh[34];
+        const BandArgs<float>& Af = reinterpret_cast<const BandArgs<float>&>(A);
+        for (int w0 = 0; w0 < tot; w0 += nth * 32) {
+            unsigned idx[32]; unsigned kept = 0u;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int w = w0 + e * nth + tid;
+                idx[e] = 0u;
+                if (w < tot) {
+                    const int i = w / nc, c = w - i * nc;
+                    const Cx<T> v = X[i * G.C + c];
+                    idx[e] = ((unsigned)i << 16) | (unsigned)(c0 + c);
+                    if (v.x != T(0) || v.y != T(0)) kept |= 1u << e;
+                }
+            }
+            record_support<32>(Af, s, idx, kept, rec_sh);
+        }
     }
     __syncthreads();
     Cx<T>* Y = line_fft<+1, T>(X, other, tg, ax1, tid, nth);
@@ -280,10 +442,14 @@ __global__ void k_rows_generic(const __grid_constant__ PocsGeom G, const __grid_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_s[32];
     __shared__ unsigned long long red_n[32];
-    const int s = blockIdx.y;
+    const int s = band_slice(A);
     const int tid = threadIdx.x, nth = blockDim.x;
-    if (MODE == 1) { if (A.stop[s] != 0) return; }
+    if (MODE == 1) { if (A.stop[s] != 0 || slice_frozen(A, s)) return; }
     if (MODE == 0 && A.adaptive) { if (A.stop[s] != 0) return; }
+    // complex128 restart launch: the iteration rebuilt is the one before the slice's switch
+    const int kk = (MODE == 1 && A.restart) ? A.esc[s] - 2 : A.k;
+    if (MODE == 1 && sizeof(T) == 4 && A.astart && blockIdx.x == 0 && tid == 0)
+        A.astart[(long long)s * (A.niter + 1) + A.k + 1] = A.acnt[s];      // end of this iteration's support record
 
     const int r0 = blockIdx.x * G.RB;
     const int nr = min(G.RB, G.n1 - r0);
@@ -302,7 +468,21 @@ __global__ void k_rows_generic(const __grid_constant__ PocsGeom G, const __grid_
     if (MODE == 0) {
         for (int w = tid; w < tot; w += nth) {
             const int rr = w / G.n2, j = w - rr * G.n2;
-            Cx<T> d = A.D[row_off + (long long)rr * G.n2 + j];
+            const long long g = row_off + (long long)rr * G.n2 + j;
+            Cx<T> d;
+            if (A.D32) { const Cx<float> t = A.src_out ? A.OUT32[g] : A.D32[g]; d = cmake<T>((T)t.x, (T)t.y); }
+            else d = A.D[g];
+            if (A.src_out) {
+                // hand-over of an fp32 iterate x_k: plain row FFT, or the APOCS step with x_old = x_k (functions/POCS.py:572-575)
+                if (A.adaptive) {
+                    const Cx<float> t = A.D32[g];
+                    const Cx<T> dd = cmake<T>((T)t.x, (T)t.y);
+                    const T m = (T)A.mask[mask_off + (long long)rr * G.n2 + j];
+                    const T keep = T(1) - A.alpha * m, om = T(1) - A.alpha;
+                    const Cx<T> xt = cmake<T>(A.alpha * dd.x + keep * d.x, A.alpha * dd.y + keep * d.y);
+                    d = cmake<T>(xt.x + om * (dd.x - m * d.x), xt.y + om * (dd.y - m * d.y));
+                }
+            } else
             if (!A.adaptive) {
                 nnz += (d.x != T(0) || d.y != T(0)) ? 1ull : 0ull;
                 part += (double)sqrt(d.x * d.x + d.y * d.y);
@@ -328,13 +508,18 @@ __global__ void k_rows_generic(const __grid_constant__ PocsGeom G, const __grid_
         for (int w = tid; w < tot; w += nth) {
             const int rr = w / G.n2, j = w - rr * G.n2;
             const long long g = (long long)rr * G.n2 + j;
-            const Cx<T> d = A.D[row_off + g];
+            Cx<T> d;
+            if (A.D32) { const Cx<float> t = A.D32[row_off + g]; d = cmake<T>((T)t.x, (T)t.y); }
+            else d = A.D[row_off + g];
             const T m = (T)A.mask[mask_off + g];
             const T coef = (T(1) - A.alpha * m) * A.inv_n;
             const Cx<T> y = cur[rr * G.pitch2 + j];
             Cx<T> x = cmake<T>(fma(coef, y.x, A.alpha * d.x), fma(coef, y.y, A.alpha * d.y));
             part += (double)sqrt(x.x * x.x + x.y * x.y);
-            if (A.write_out) A.OUT[row_off + g] = x;
+            if (A.write_out) {
+                if (A.OUT32) A.OUT32[row_off + g] = cmake<float>((float)x.x, (float)x.y);
+                else A.OUT[row_off + g] = x;
+            }
             if (A.adaptive) {
                 const T keep = T(1) - A.alpha * m;
                 Cx<T> xt = cmake<T>(A.alpha * d.x + keep * x.x, A.alpha * d.y + keep * x.y);
@@ -362,7 +547,7 @@ __global__ void k_rows_generic(const __grid_constant__ PocsGeom G, const __grid_
                     atomicAdd(&A.stats[s].nnz, c);
                 }
             } else {
-                atomicAdd(&A.S[(long long)s * (A.niter + 1) + A.k + 1], v);
+                atomicAdd(&A.S[(long long)s * (A.niter + 1) + kk + 1], v);
             }
         }
     }

@@ -43,7 +43,7 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     const Cx<float>* __restrict__ Bi = Bf + M;
     const int* __restrict__ perm = reinterpret_cast<const int*>(Bi + M);
     const int* __restrict__ kperm = perm + M;
-    const int s = blockIdx.y;
+    const int s = band_slice(A);
     const int tid = threadIdx.x;
     const int c = tid % C, j = tid / C;
     const int col = blockIdx.x * C + c;
@@ -75,7 +75,7 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     Cx<float> tau = cmake<float>(0.f, 0.f);
     if (MODE == 1) {
         tau = A.tau[(long long)s * A.niter + A.k];
-        if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
+        if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps) || slice_escalated(A, s)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
     }
     if (bulk) {
         asm volatile("cp.async.wait_all;");
@@ -127,6 +127,14 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     // ---- threshold (or kx-ky filter) in Rader order
     const float a = tau.x, b = tau.y;
     const float t2re = a * a - b * b, t2im = 2.f * a * b;
+    if (A.guard && op != P3D_OP_FILTER) {
+        GuardBand<float> gb(A, s, a, b, op);
+#pragma unroll
+        for (int e = 0; e < E; ++e) gb.test(v[e]);
+        if (j == 0) gb.test(dc);
+        if (!ok) gb.hit = false;
+        gb.commit(A, s);
+    }
     if (op == P3D_OP_HARD && !A.exact_tie) {
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float, false>(v[e], a, b, t2re, t2im);
@@ -152,6 +160,20 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
         }
         const float h0 = (ok && j == 0) ? __ldg(H) : 0.f;
         dc = cmake<float>(dc.x * h0, dc.y * h0);
+    }
+
+    if (A.arena && op != P3D_OP_FILTER) {
+        // support record of the fp32 pilot (exact restart): natural frequency row of every surviving coefficient
+        __shared__ int rec_sh[34];
+        unsigned idx[E + 1]; unsigned kept = 0u;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            idx[e] = ((unsigned)__ldg(kperm + j + e * T) << 16) | (unsigned)col;
+            if (ok && (v[e].x != 0.f || v[e].y != 0.f)) kept |= 1u << e;
+        }
+        idx[E] = (unsigned)col;
+        if (ok && j == 0 && (dc.x != 0.f || dc.y != 0.f)) kept |= 1u << E;
+        record_support<E + 1>(A, s, idx, kept, rec_sh);
     }
 
     // ---- inverse DFT of length P (unscaled): h[m] = Y[g^-m] is already in natural order of m
@@ -264,8 +286,9 @@ k_rows_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     const Cx<float>* __restrict__ B2 = B1 + M;
     const int* __restrict__ perm = reinterpret_cast<const int*>(B2 + M);
     const int* __restrict__ kperm = perm + M;
-    const int s = blockIdx.y, row = blockIdx.x, j = threadIdx.x;
+    const int s = band_slice(A), row = blockIdx.x, j = threadIdx.x;
     const int stopped = A.stop[s];
+
     const long long base = ((long long)s * G.n1 + row) * P;
     Cx<float>* __restrict__ Wp = A.W + base;
     const Cx<float>* __restrict__ Dp = A.D + base;
@@ -274,7 +297,8 @@ k_rows_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     Cx<float>* land = acc.line(1);                                       // W row, natural order (free until exchange 2)
     Cx<float>* dst = reinterpret_cast<Cx<float>*>(smem_raw) + 2 * MP::LINE;   // observed row, natural order
     for (int i = j; i < P; i += T) { land[i] = Wp[i]; dst[i] = Dp[i]; }
-    if (stopped != 0) return;
+    if (stopped != 0 || slice_frozen(A, s)) return;
+    if (A.astart && row == 0 && j == 0) A.astart[(long long)s * (A.niter + 1) + A.k + 1] = A.acnt[s];
     __syncthreads();
 
     Cx<float> v[E];

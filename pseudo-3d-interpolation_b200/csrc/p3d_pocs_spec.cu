@@ -127,8 +127,11 @@ typedef LinePlan<256, 8, 8, 8, 4> LP256E8;
 typedef LinePlan<200, 10, 10, 10, 2> LP200E10;
 
 #define P3D_COLS64(LP, C, MINB, NAME) do { k.cols_iter = launch_cols<LP, C, MINB, false, double>; \
+                                           k.cols_stats = launch_cols_stats64<LP, C, MINB>; k.cols_C = C; \
                                            k.cols_name = NAME; k.cols_radices = radices_of<LP>(); } while (0)
 #define P3D_ROWS64(LP, RB, MINB, NAME) do { k.rows_iter = launch_rows<LP, RB, MINB, false, double>; \
+                                            k.rows_iter_io32 = launch_rows<LP, RB, MINB, false, double, true>; \
+                                            k.rows_init_io32 = launch_rows_init<LP, RB, MINB, double>; \
                                             k.rows_name = NAME; k.rows_radices = radices_of<LP>(); \
                                             k.pack_mask = launch_pack<LP>; k.rows_T = LP::T; } while (0)
 

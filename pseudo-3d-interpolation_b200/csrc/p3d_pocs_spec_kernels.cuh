@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A, const int op) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
-    const int s = blockIdx.y;
+    const int s = band_slice(A);
     const int tid = threadIdx.x;
     const int c = tid % C, j = tid / C;
     const int col = blockIdx.x * C + c;
@@ -68,7 +68,7 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     const Cx<F> tau = A.tau[(long long)s * A.niter + A.k];
     // the (rare) early-exit test comes AFTER the loads were issued, so that its own dependent
     // loads (stop flag, two sums) do not delay them
-    if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
+    if ((!A.restart && slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) || slice_escalated(A, s)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
     if (bulk) {
         asm volatile("cp.async.wait_all;");
         __syncthreads();
@@ -77,10 +77,27 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
         for (int e = 0; e < E; ++e) v[e] = land[(j + e * T) * C];
     }
 
+    if (sizeof(F) == 8 && op == P3D_OP_RESTART) {
+        // exact restart of the escalating mode: the tile holds a thresholded spectrum, inverse transform only
+        LP::template fft<+1, 0, F>(v, acc, j, tw);
+        if (ok) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) Ws[(long long)(j + e * T) * G.n2] = v[e];
+        }
+        return;
+    }
+
     LP::template fft<-1, 0, F>(v, acc, j, tw);
 
     const F a = tau.x, b = tau.y;
     const F t2re = a * a - b * b, t2im = F(2) * a * b;
+    if (sizeof(F) == 4 && A.guard && op != P3D_OP_FILTER) {
+        GuardBand<F> gb(A, s, a, b, op);
+#pragma unroll
+        for (int e = 0; e < E; ++e) gb.test(v[e]);
+        if (!ok) gb.hit = false;
+        gb.commit(A, s);
+    }
     if (op == P3D_OP_HARD && !A.exact_tie) {
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, F, false>(v[e], a, b, t2re, t2im);
@@ -99,6 +116,17 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
 #pragma unroll
         for (int e = 0; e < E; ++e) { const F h = ok ? (F)__ldg(H + (long long)(j + e * T) * G.n2) : F(0); v[e] = cmake<F>(v[e].x * h, v[e].y * h); }
     }
+    if (sizeof(F) == 4 && A.arena && op != P3D_OP_FILTER) {
+        // support record of the fp32 pilot (exact restart): which coefficients survived the threshold
+        __shared__ int rec_sh[34];
+        unsigned idx[E]; unsigned kept = 0u;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            idx[e] = ((unsigned)(j + e * T) << 16) | (unsigned)col;
+            if (ok && (v[e].x != F(0) || v[e].y != F(0))) kept |= 1u << e;
+        }
+        record_support<E>(reinterpret_cast<const BandArgs<float>&>(A), s, idx, kept, rec_sh);
+    }
 
     LP::template fft<+1, (LP::NEXCH & 1), F>(v, acc, j, tw);
 
@@ -109,14 +137,27 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
 }
 
 // ---- row kernel ----------------------------------------------------------------------------------
-template <typename F, typename LP, int RB, int MINB, bool PF>
+// observed data / result pointers of the row kernels: the state's own type, or complex64 beside a complex128 state (IO32)
+template <bool IO32, typename F> struct IoSel {
+    typedef F T;
+    __device__ __forceinline__ static const Cx<F>* d(const BandArgs<F>& A) { return A.D; }
+    __device__ __forceinline__ static Cx<F>* o(const BandArgs<F>& A) { return A.OUT; }
+};
+template <typename F> struct IoSel<true, F> {
+    typedef float T;
+    __device__ __forceinline__ static const Cx<float>* d(const BandArgs<F>& A) { return A.D32; }
+    __device__ __forceinline__ static Cx<float>* o(const BandArgs<F>& A) { return A.OUT32; }
+};
+
+template <typename F, typename LP, int RB, int MINB, bool PF, bool IO32 = false>
 __global__ void __launch_bounds__(LP::T* RB, MINB)
 k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_s[32];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     static_assert(E <= 32, "mask bits are packed into one 32-bit word");
-    const int s = blockIdx.y;
+    typedef typename IoSel<IO32, F>::T FD;
+    const int s = band_slice(A);
     const int stopped = A.stop[s];
     const int tid = threadIdx.x;
     const int j = tid % T, rr = tid / T;
@@ -125,8 +166,10 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     const long long off = (long long)s * G.n1 * N + (long long)row * N + j;
     RowAcc<F, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<F>*>(smem_raw) + rr * LP::LINE;
     Cx<F>* __restrict__ Wp = A.W + off;
-    const Cx<F>* __restrict__ Dp = A.D + off;
-    Cx<F>* __restrict__ Op = A.OUT + off;
+    const Cx<FD>* __restrict__ Dp = IoSel<IO32, F>::d(A) + off;
+    Cx<FD>* __restrict__ Op = IoSel<IO32, F>::o(A) + off;
+    // complex128 restart launch: the iteration rebuilt is the one before the slice's switch
+    const int kk = A.restart ? A.esc[s] - 2 : A.k;
 
     Cx<F> v[E];
 #pragma unroll
@@ -138,7 +181,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
         for (int e = 0; e < E; ++e) prefetch_l2(Dp + e * T);
         const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + P3D_PREFETCH_DISTANCE;
         const long long by = lin / gridDim.x, bx = lin - by * gridDim.x;
-        if (by < gridDim.y && bx * RB + rr < G.n1) {
+        if (!A.list && by < gridDim.y && bx * RB + rr < G.n1) {
             const Cx<F>* nx = A.W + by * (long long)G.n1 * N + (bx * RB + rr) * (long long)N + j;
 #pragma unroll
             for (int e = 0; e < E; ++e) prefetch_l2(nx + e * T);
@@ -147,7 +190,9 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     // one packed mask word per thread (bit e <-> column j + e*T) rides along with the first loads
     const long long midx = (A.first_slice + s) / G.slices_per_mask;
     const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
-    if (stopped != 0) return;
+    if (stopped != 0 || slice_frozen(A, s)) return;
+    if (sizeof(F) == 4 && A.astart && blockIdx.x == 0 && tid == 0)
+        A.astart[(long long)s * (A.niter + 1) + A.k + 1] = A.acnt[s];          // end of this iteration's support record
 
     LP::template fft<+1, 0, F>(v, acc, j, tw);
 
@@ -156,14 +201,14 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
         // all observed-data loads are issued before the first use (one exposed latency, not E)
         Cx<F> d[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) d[e] = Dp[e * T];
+        for (int e = 0; e < E; ++e) { const Cx<FD> t = Dp[e * T]; d[e] = cmake<F>((F)t.x, (F)t.y); }
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const F m = ((mbits >> e) & 1u) ? F(1) : F(0);
             const F coef = (F(1) - A.alpha * m) * A.inv_n;
             Cx<F> x = cmake<F>(fma(coef, v[e].x, A.alpha * d[e].x), fma(coef, v[e].y, A.alpha * d[e].y));
             part += sqrt(x.x * x.x + x.y * x.y);
-            if (A.write_out) Op[e * T] = x;
+            if (A.write_out) Op[e * T] = cmake<FD>((FD)x.x, (FD)x.y);
             if (A.adaptive) {
                 const F keep = F(1) - A.alpha * m, om = F(1) - A.alpha;
                 const Cx<F> xt = cmake<F>(A.alpha * d[e].x + keep * x.x, A.alpha * d[e].y + keep * x.y);
@@ -181,7 +226,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
         constexpr int NW = (T * RB + 31) / 32;
         double t = tid < NW ? red_s[tid] : 0.0;
         t = warp_sum(t);
-        if (tid == 0) atomicAdd(&A.S[(long long)s * (A.niter + 1) + A.k + 1], t);
+        if (tid == 0) atomicAdd(&A.S[(long long)s * (A.niter + 1) + kk + 1], t);
     }
     if (A.last) return;
 
@@ -194,45 +239,56 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
 }
 
 // ---- once-per-slice kernels: row FFT of the observed slice, column FFT + schedule statistics -------
-template <typename LP, int RB, int MINB>
+// F = float: the observed slice A.D.  F = double (IO32): complex64 source = the observed slice A.D32 or, with
+// A.src_out, the fp32 iterate x_k that the escalating mode hands over in A.OUT32.
+template <typename F, typename LP, int RB, int MINB>
 __global__ void __launch_bounds__(LP::T* RB, MINB)
-k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A) {
+k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_s[32];
     __shared__ unsigned long long red_n[32];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
-    const int s = blockIdx.y;
+    constexpr bool IO32 = sizeof(F) == 8;
+    const int s = band_slice(A);
     if (A.adaptive && A.stop[s] != 0) return;
     const int tid = threadIdx.x;
     const int j = tid % T, rr = tid / T;
     const int row = blockIdx.x * RB + rr;
     const bool ok = row < G.n1;
     const long long off = (long long)s * G.n1 * N + (long long)row * N + j;
-    RowAcc<float, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + rr * LP::LINE;
-    const Cx<float>* __restrict__ Dp = A.D + off;
-    Cx<float>* __restrict__ Wp = A.W + off;
-    Cx<float> v[E];
+    RowAcc<F, RB, LP::LINE> acc; acc.base = reinterpret_cast<Cx<F>*>(smem_raw) + rr * LP::LINE;
+    const Cx<float>* __restrict__ Dp = (IO32 ? A.D32 : reinterpret_cast<const Cx<float>*>(A.D)) + off;
+    Cx<F>* __restrict__ Wp = A.W + off;
+    Cx<F> v[E];
+    if (IO32 && A.src_out) {
+        const Cx<float>* __restrict__ Xp = A.OUT32 + off;
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = ok ? Dp[e * T] : cmake<float>(0.f, 0.f);
-    float part = 0.f;
+        for (int e = 0; e < E; ++e) { const Cx<float> t = ok ? Xp[e * T] : cmake<float>(0.f, 0.f); v[e] = cmake<F>((F)t.x, (F)t.y); }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const Cx<float> t = ok ? Dp[e * T] : cmake<float>(0.f, 0.f); v[e] = cmake<F>((F)t.x, (F)t.y); }
+    }
+    F part = F(0);
     unsigned long long nnz = 0ull;
     if (!A.adaptive) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            nnz += (v[e].x != 0.f || v[e].y != 0.f) ? 1ull : 0ull;
-            part += sqrtf(v[e].x * v[e].x + v[e].y * v[e].y);
+            nnz += (v[e].x != F(0) || v[e].y != F(0)) ? 1ull : 0ull;
+            part += sqrt(v[e].x * v[e].x + v[e].y * v[e].y);
         }
     } else {
-        // APOCS prologue with x_old = x (functions/POCS.py:572-575)
+        // APOCS prologue (functions/POCS.py:572-575) with x_old = x, or x_old = the iterate handed over
         const long long midx = (A.first_slice + s) / G.slices_per_mask;
         const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const float m = ((mbits >> e) & 1u) ? 1.f : 0.f;
-            const float keep = 1.f - A.alpha * m, om = 1.f - A.alpha;
-            const Cx<float> d = v[e];
-            const Cx<float> xt = cmake<float>(A.alpha * d.x + keep * d.x, A.alpha * d.y + keep * d.y);
-            v[e] = cmake<float>(xt.x + om * (d.x - m * d.x), xt.y + om * (d.y - m * d.y));
+            const F m = ((mbits >> e) & 1u) ? F(1) : F(0);
+            const F keep = F(1) - A.alpha * m, om = F(1) - A.alpha;
+            const Cx<F> xo = v[e];
+            Cx<F> d = xo;
+            if (IO32 && A.src_out) { const Cx<float> t = ok ? Dp[e * T] : cmake<float>(0.f, 0.f); d = cmake<F>((F)t.x, (F)t.y); }
+            const Cx<F> xt = cmake<F>(A.alpha * d.x + keep * xo.x, A.alpha * d.y + keep * xo.y);
+            v[e] = cmake<F>(xt.x + om * (d.x - m * xo.x), xt.y + om * (d.y - m * xo.y));
         }
     }
     if (A.accum) {
@@ -251,11 +307,58 @@ k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict
             if (tid == 0) { atomicAdd(&A.S[(long long)s * (A.niter + 1)], t); atomicAdd(&A.stats[s].nnz, c); }
         }
     }
-    LP::template fft<-1, 0, float>(v, acc, j, tw);
+    LP::template fft<-1, 0, F>(v, acc, j, tw);
     if (ok) {
 #pragma unroll
         for (int e = 0; e < E; ++e) Wp[e * T] = v[e];
     }
+}
+
+// complex128 statistics of X0 (escalating mode): exact lexicographic maximum per CTA (A.cand), sum |X0|^2, max / min |X0|
+template <typename LP, int C, int MINB>
+__global__ void __launch_bounds__(LP::T* C, MINB)
+k_cols_stats_spec64(const __grid_constant__ PocsGeom G, const Cx<double>* __restrict__ tw, const __grid_constant__ BandArgs<double> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int E = LP::E, T = LP::T, N = LP::N;
+    const int s = band_slice(A);
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    const int col = blockIdx.x * C + c;
+    const bool ok = col < G.n2;
+    const Cx<double>* __restrict__ Ws = A.W + (long long)s * N * G.n2 + col;
+    ColAcc<double, C, LP::LINE> acc; acc.base = reinterpret_cast<Cx<double>*>(smem_raw) + c;
+    Cx<double> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(j + e * T) * G.n2] : cmake<double>(0.0, 0.0);
+    LP::template fft<-1, 0, double>(v, acc, j, tw);
+    if (A.store_x0_inplace && ok) {
+        Cx<double>* __restrict__ Wo = A.W + (long long)s * N * G.n2 + col;
+#pragma unroll
+        for (int e = 0; e < E; ++e) Wo[(long long)(j + e * T) * G.n2] = v[e];
+    }
+    double bre = -INFINITY, bim = -INFINITY, ss = 0.0;
+    unsigned long long ak = 0ull, ik = ~0ull;
+    if (ok) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (v[e].x > bre || (v[e].x == bre && v[e].y > bim)) { bre = v[e].x; bim = v[e].y; }
+            const double r2 = v[e].x * v[e].x + v[e].y * v[e].y;
+            ss += r2;
+            const unsigned long long k2 = f64_ordered(sqrt(r2));
+            ak = k2 > ak ? k2 : ak; ik = k2 < ik ? k2 : ik;
+        }
+    }
+    ss = warp_sum(ss); ak = warp_max_u64(ak);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w2 = __shfl_xor_sync(0xffffffffu, ik, o); ik = w2 < ik ? w2 : ik; }
+    if ((tid & 31) == 0) {
+        atomicAdd(&A.stats[s].sumsq, ss);
+        atomicMax(&A.stats[s].maxabs64_key, ak);
+        atomicMin(&A.stats[s].minabs64_key, ik);
+    }
+    __syncthreads();          // the exchange buffers are free now: reuse them for the block reduction
+    block_lexmax(bre, bim, reinterpret_cast<double*>(smem_raw));
+    if (tid == 0) A.cand[(long long)s * A.cand_stride + blockIdx.x] = make_double2(bre, bim);
 }
 
 template <typename LP, int C, int MINB>
@@ -263,7 +366,7 @@ __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_stats_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
-    const int s = blockIdx.y;
+    const int s = band_slice(A);
     const int tid = threadIdx.x;
     const int c = tid % C, j = tid / C;
     const int col = blockIdx.x * C + c;
@@ -323,27 +426,38 @@ static void launch_cols(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A
     dim3 grid((G.n2 + C - 1) / C, ns);
     k_cols_spec<F, LP, C, MINB, BULK, SB><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
 }
-template <typename LP, int RB, int MINB, bool PF = false, typename F = float>
+template <typename LP, int RB, int MINB, bool PF = false, typename F = float, bool IO32 = false>
 static void launch_rows(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A, int ns, cudaStream_t st) {
     constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<F>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_rows_spec<F, LP, RB, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_rows_spec<F, LP, RB, MINB, PF, IO32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n1 + RB - 1) / RB, ns);
-    k_rows_spec<F, LP, RB, MINB, PF><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+    k_rows_spec<F, LP, RB, MINB, PF, IO32><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
 }
-template <typename LP, int RB, int MINB>
-static void launch_rows_init(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {
-    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<float>);
+template <typename LP, int RB, int MINB, typename F = float>
+static void launch_rows_init(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A, int ns, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * RB * sizeof(Cx<F>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_rows_init_spec<LP, RB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_rows_init_spec<F, LP, RB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n1 + RB - 1) / RB, ns);
-    k_rows_init_spec<LP, RB, MINB><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+    k_rows_init_spec<F, LP, RB, MINB><<<grid, LP::T * RB, smem, st>>>(G, tw, A);
+}
+template <typename LP, int C, int MINB>
+static void launch_cols_stats64(const PocsGeom& G, const Cx<double>* tw, const BandArgs<double>& A, int ns, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * LP::LINE * C * sizeof(Cx<double>);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_cols_stats_spec64<LP, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid((G.n2 + C - 1) / C, ns);
+    k_cols_stats_spec64<LP, C, MINB><<<grid, LP::T * C, smem, st>>>(G, tw, A);
 }
 template <typename LP, int C, int MINB>
 static void launch_cols_stats(const PocsGeom& G, const Cx<float>* tw, const BandArgs<float>& A, int ns, cudaStream_t st) {

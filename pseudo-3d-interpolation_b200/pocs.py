@@ -30,7 +30,7 @@ from . import _lib
 TRANSFORMS = ("FFT", "WAVELET", "SHEARLET", "CURVELET", "DCT")
 
 __all__ = ["POCS_algorithm", "POCS", "FPOCS", "APOCS", "get_threshold_decay", "threshold", "pocs_cube",
-           "PocsPlan", "make_params", "mask_from_fold", "fft2", "ifft2", "set_default_precision"]
+           "PocsPlan", "make_params", "mask_from_fold", "fft2", "ifft2", "set_default_precision", "release_plans"]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -112,9 +112,12 @@ def mask_from_fold(fold):
 class PocsPlan:
     """One ``p3d_plan`` (one GPU, one slice shape).  Not re-entrant; use one per thread/GPU."""
 
-    def __init__(self, n_iline, n_xline, device=0, max_slices=0, band_slices=0, precision=32):
-        """``precision``: 32 = fp32 fast path (default); 64 = float64 state mode (complex128
-        iterate on the device, result rounded once to complex64) for bit-level-robust parity."""
+    def __init__(self, n_iline, n_xline, device=0, max_slices=0, band_slices=0, precision=0):
+        """``precision``: 0 / "auto" (default) = escalating: every slice iterates in fp32 until a coefficient of its
+        spectrum comes within a guard band of the threshold and in complex128 from that iterate on (within 1e-4 of the
+        float64 reference); 32 = fp32 only (fastest; threshold decisions can differ from float64 in the late
+        iterations); 64 = float64 state mode (complex128 throughout, result rounded once to complex64)."""
+        precision = _precision_code(precision)
         lib = _lib.load()
         _lib.require_gpu()
         self.n_iline, self.n_xline, self.device = int(n_iline), int(n_xline), int(device)
@@ -123,8 +126,13 @@ class PocsPlan:
         self._h = h
         self._lock = threading.Lock()
         self.precision = int(precision)
-        if self.precision != 32:
-            self.set_option("precision", self.precision)
+        self.set_option("precision", self.precision)
+
+    def escalation(self):
+        """(slices that switched to complex128, slice-iterations they ran there) of the last run."""
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().p3d_plan_get_escalation(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -186,6 +194,9 @@ class PocsPlan:
             raise ValueError("not enough masks for the given slices_per_mask")
         if out is None:
             out = np.empty_like(x)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.complex64 and out.shape == x.shape and out.flags.c_contiguous
+                  and out.flags.writeable):
+            raise ValueError("out must be a writeable C-contiguous complex64 array of the shape of x")
         nit = np.zeros(ns, dtype=np.int32)
         cost = np.zeros(ns, dtype=np.float64)
         costs = np.full((ns, params.niter), np.nan, dtype=np.float64) if want_costs else None
@@ -246,21 +257,36 @@ class PocsPlan:
         return out[0] if x.ndim == 2 else out
 
 
+def _precision_code(p):
+    if isinstance(p, str):
+        p = {"auto": 0, "escalating": 0, "0": 0, "32": 32, "64": 64}.get(p.strip().lower(), p)
+    if p not in (0, 32, 64):
+        raise ValueError('precision must be "auto" (0), 32 or 64')
+    return int(p)
+
+
 _PLANS = {}
 _PLANS_LOCK = threading.Lock()
-_DEFAULT_PRECISION = [int(os.environ.get("P3D_PRECISION", "32"))]
+_DEFAULT_PRECISION = [_precision_code(os.environ.get("P3D_PRECISION", "auto"))]
 
 
-def set_default_precision(bits: int):
-    """32 (fp32 fast path) or 64 (float64 state mode) for POCS_algorithm / pocs_cube calls that do
-    not say otherwise.  Also settable with the environment variable P3D_PRECISION."""
-    if int(bits) not in (32, 64):
-        raise ValueError("precision must be 32 or 64")
-    _DEFAULT_PRECISION[0] = int(bits)
+def set_default_precision(bits):
+    """"auto" / 0 (escalating fp32 -> complex128, the default), 32 (fp32 only) or 64 (float64 state mode) for
+    POCS_algorithm / pocs_cube calls that do not say otherwise.  Also settable with the environment variable
+    P3D_PRECISION."""
+    _DEFAULT_PRECISION[0] = _precision_code(bits)
+
+
+def release_plans():
+    """Destroy the cached plans (and with them their device buffers, which are sized for the largest call so far)."""
+    with _PLANS_LOCK:
+        for p in _PLANS.values():
+            p.close()
+        _PLANS.clear()
 
 
 def get_plan(n_iline, n_xline, device=0, precision=None) -> PocsPlan:
-    precision = _DEFAULT_PRECISION[0] if precision is None else int(precision)
+    precision = _DEFAULT_PRECISION[0] if precision is None else _precision_code(precision)
     key = (int(n_iline), int(n_xline), int(device), precision)
     with _PLANS_LOCK:
         p = _PLANS.get(key)
@@ -486,7 +512,10 @@ def pocs_cube(cube, fold_or_mask, devices=None, out=None, results=None, precisio
     if mask.shape != (n1, n2):
         raise ValueError(f"mask shape {mask.shape} does not match slices ({n1}, {n2})")
     xin = cube if cube.dtype == np.complex64 else cube.astype(np.complex64)
-    res = out if (out is not None and out.dtype == np.complex64) else np.empty((ns, n1, n2), dtype=np.complex64)
+    # the caller's `out` is written in place only when it is a dense complex64 array of the right shape
+    direct = (out is not None and isinstance(out, np.ndarray) and out.dtype == np.complex64 and out.shape == (ns, n1, n2)
+              and out.flags.c_contiguous and out.flags.writeable)
+    res = out if direct else np.empty((ns, n1, n2), dtype=np.complex64)
     nit = np.zeros(ns, dtype=np.int32)
     cost = np.zeros(ns, dtype=np.float64)
     if devices is None:
