@@ -47,6 +47,7 @@ struct Lane {
     unsigned* arena = nullptr; int* acnt = nullptr; int* astart = nullptr; int* h_astart = nullptr; double2* yval = nullptr;
     int arena_cap = 0;
     int64_t n_escalated = 0, n_esc_iters = 0;
+    unsigned long long* dd_keys = nullptr; unsigned int* dd_vals = nullptr; int64_t dd_ne = 0;   // exact data-driven schedule scratch
     // CUB scratch of the data-driven schedule (per lane: lanes sort concurrently on their own streams)
     void* cub_temp = nullptr; size_t cub_temp_bytes = 0;
     std::vector<EventPair> events;      // profiling events of this lane's launches
@@ -159,6 +160,9 @@ void free_lane(Lane& L) {
     if (L.h_guard) cudaFreeHost(L.h_guard);
     if (L.h_list) cudaFreeHost(L.h_list);
     if (L.cub_temp) cudaFree(L.cub_temp);
+    if (L.dd_keys) cudaFree(L.dd_keys);
+    if (L.dd_vals) cudaFree(L.dd_vals);
+    L.dd_keys = nullptr; L.dd_vals = nullptr; L.dd_ne = 0;
     L.cub_temp = nullptr; L.cub_temp_bytes = 0; L.cand_stride = 0;
     L.W64 = L.tau64 = L.h_tau64 = nullptr; L.esc = L.h_esc = L.list = L.h_list = nullptr; L.guard = L.h_guard = nullptr; L.cand = nullptr;
     L.has_esc = false;
@@ -329,6 +333,56 @@ __global__ void k_pick_tau(const unsigned long long* sorted_desc, const SliceSta
         if (idx > (long long)nv - 1) idx = (long long)nv - 1;
         const unsigned long long key = sorted_desc[idx];
         tau[k] = cmake<float>(f32_from_ordered((unsigned int)(key >> 32)), f32_from_ordered((unsigned int)(key & 0xffffffffu)));
+    }
+}
+
+// ---- data-driven schedule from the complex128 X0 (escalating mode): exact order statistics in numpy's ordering ----
+// key = ordered real part of the candidates inside (tau_min, tau_max) (lexicographic bounds), 0 for everything else
+__global__ void k_dd_keys64(const Cx<double>* __restrict__ X0, long long n, double lo_re, double lo_im, double hi_re, double hi_im,
+                            unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals, SliceStats* st) {
+    unsigned long long cnt = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const Cx<double> v = X0[i];
+        const bool above_lo = (lo_re < v.x) || (lo_re == v.x && lo_im < v.y);
+        const bool below_hi = (v.x < hi_re) || (v.x == hi_re && v.y < hi_im);
+        const bool in = above_lo && below_hi;
+        keys[i] = in ? f64_ordered(v.x) : 0ull;
+        vals[i] = (unsigned int)i;
+        cnt += in ? 1ull : 0ull;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&st->n_cand, cnt);
+}
+// tau_k = V[ceil(k (Nv - 1) / (niter - 1))] of the descending lexicographic order V; equal real parts (Hermitian spectra
+// of real slices) are ordered by their imaginary parts inside the run
+__global__ void k_pick_tau64(const unsigned long long* __restrict__ skeys, const unsigned int* __restrict__ svals, const Cx<double>* __restrict__ X0,
+                             const SliceStats* st, Cx<double>* tau64, int niter) {
+    const long long nv = (long long)st->n_cand;
+    for (int k = threadIdx.x; k < niter; k += blockDim.x) {
+        if (nv == 0) { tau64[k] = cmake<double>(nan(""), nan("")); continue; }
+        long long idx = 0;
+        if (k > 0) idx = (long long)ceil((double)((long long)k * (nv - 1)) / (double)(niter - 1));
+        if (idx > nv - 1) idx = nv - 1;
+        const unsigned long long key = skeys[idx];
+        long long a = idx, b = idx + 1;
+        while (a > 0 && skeys[a - 1] == key) --a;
+        while (b < nv && skeys[b] == key) ++b;
+        Cx<double> pick = X0[svals[idx]];
+        if (b - a > 1) {
+            // rank (idx - a) by descending imaginary part inside the run of equal real parts
+            const long long want = idx - a;
+            for (long long c = a; c < b; ++c) {
+                const double im = X0[svals[c]].y;
+                long long larger = 0, equal_before = 0;
+                for (long long e = a; e < b; ++e) {
+                    const double ime = X0[svals[e]].y;
+                    if (ime > im) ++larger;
+                    else if (ime == im && e < c) ++equal_before;
+                }
+                if (larger + equal_before == want) { pick = X0[svals[c]]; break; }
+            }
+        }
+        tau64[k] = pick;
     }
 }
 
@@ -899,11 +953,8 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     // ---- setup: row FFT of d (fp32 state), statistics of X0 in complex128 (X0 stays in W64 for the replay) -----------
     {
         BandArgs<float> B = A;
-        B.adaptive = 0; B.accum = 1; B.store_x0 = data_driven ? 1 : 0;
-        for_list32(B, L.list, (int)count, [&](const BandArgs<float>& b, int nb) {
-            launch_rows_init(P, L, b, nb);
-            if (data_driven) launch_cols_stats(P, L, b, nb);
-        });
+        B.adaptive = 0; B.accum = 1; B.store_x0 = 0;
+        for_list32(B, L.list, (int)count, [&](const BandArgs<float>& b, int nb) { launch_rows_init(P, L, b, nb); });
         BandArgs<double> B64 = A64;
         B64.adaptive = 0; B64.accum = 0; B64.src_out = 0; B64.store_x0_inplace = 1;
         rows_init64(B64, L.list, (int)count);
@@ -937,23 +988,36 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
         const double g = gfac * eps32 * std::sqrt(ss.sumsq / (double)std::max<unsigned long long>(1ull, ss.nnz));
         return (float)std::min(g, 3.0e38);
     };
+    auto stats64 = [&](const SliceStats& ss) {
+        ScheduleStats sc;
+        sc.z = cd(f64_from_ordered(ss.re64_key), f64_from_ordered(ss.im64_key));
+        sc.sumsq = ss.sumsq; sc.vmax = f64_from_ordered(ss.maxabs64_key); sc.vmin = f64_from_ordered(ss.minabs64_key);
+        return sc;
+    };
     if (!data_driven) {
         for (int64_t i = 0; i < count; ++i) {
             const SliceStats& ss = L.h_stats[i];
             L.h_stop[i] = ss.nnz == 0 ? -1 : 0;
-            ScheduleStats sc;
-            sc.z = cd(f64_from_ordered(ss.re64_key), f64_from_ordered(ss.im64_key));
-            sc.sumsq = ss.sumsq; sc.vmax = f64_from_ordered(ss.maxabs64_key); sc.vmin = f64_from_ordered(ss.minabs64_key);
             bool is_real = false;
-            host_schedule(pr, sc, ne, tau, is_real);
+            host_schedule(pr, stats64(ss), ne, tau, is_real);
             if (pr.sqrt_decay) apply_sqrt_decay(tau, is_real);
             store_tau(i);
             L.h_guard[i] = guard_of(ss);
         }
     } else {
-        // thresholds = order statistics of the fp32 X0 (sorted on the device); the complex128 phase uses the same values
+        // thresholds = order statistics of X0 in numpy's complex ordering, taken from the complex128 X0 left in W64:
+        // radix sort of the ordered real parts (payload = position), ties resolved on the imaginary parts
+        if (L.dd_ne < ne) {
+            if (L.dd_keys) cudaFree(L.dd_keys);
+            if (L.dd_vals) cudaFree(L.dd_vals);
+            L.dd_keys = nullptr; L.dd_vals = nullptr; L.dd_ne = 0;
+            P3D_CUDA(cudaMalloc(&L.dd_keys, sizeof(unsigned long long) * 2 * ne));
+            P3D_CUDA(cudaMalloc(&L.dd_vals, sizeof(unsigned int) * 2 * ne));
+            L.dd_ne = ne;
+        }
         size_t need = 0;
-        cub::DeviceRadixSort::SortKeysDescending(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (long long)ne, 0, 64, st);
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                                  (unsigned int*)nullptr, (unsigned int*)nullptr, (long long)ne, 0, 64, st);
         if (need > L.cub_temp_bytes) {
             if (L.cub_temp) cudaFree(L.cub_temp);
             L.cub_temp = nullptr; L.cub_temp_bytes = 0;
@@ -963,20 +1027,17 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             L.h_stop[i] = L.h_stats[i].nnz == 0 ? -1 : 0;
             if (L.h_stop[i]) continue;
             cd tmin, tmax;
-            schedule_bounds(pr, stats_f32(L.h_stats[i]), ne, tmin, tmax);
-            const unsigned long long lo = lex_key((float)tmin.real(), (float)tmin.imag());
-            const unsigned long long hi = lex_key((float)tmax.real(), (float)tmax.imag());
-            unsigned long long* keys = reinterpret_cast<unsigned long long*>(OUT + i * ne);
-            unsigned long long* sorted = reinterpret_cast<unsigned long long*>(L.W + i * ne);
+            schedule_bounds(pr, stats64(L.h_stats[i]), ne, tmin, tmax);
             prof_begin(P, L.events, st, 6);
-            k_make_keys<<<std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(keys, ne, lo, hi, L.stats + i);
+            k_dd_keys64<<<std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(L.W64 + i * ne, ne, tmin.real(), tmin.imag(), tmax.real(), tmax.imag(),
+                                                                                          L.dd_keys, L.dd_vals, L.stats + i);
             size_t tb = L.cub_temp_bytes;
-            cub::DeviceRadixSort::SortKeysDescending(L.cub_temp, tb, keys, sorted, (long long)ne, 0, 64, st);
-            k_pick_tau<<<1, 128, 0, st>>>(sorted, L.stats + i, L.tau + i * niter, niter);
+            cub::DeviceRadixSort::SortPairsDescending(L.cub_temp, tb, L.dd_keys, L.dd_keys + ne, L.dd_vals, L.dd_vals + ne, (long long)ne, 0, 64, st);
+            k_pick_tau64<<<1, 128, 0, st>>>(L.dd_keys + ne, L.dd_vals + ne, L.W64 + i * ne, L.stats + i, L.tau64 + i * niter, niter);
             prof_end(P, L.events, st);
         }
         P3D_CUDA(cudaGetLastError());
-        P3D_CUDA(cudaMemcpyAsync(L.h_tau, L.tau, sizeof(Cx<float>) * count * niter, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(L.h_tau64, L.tau64, sizeof(Cx<double>) * count * niter, cudaMemcpyDeviceToHost, st));
         P3D_CUDA(cudaMemcpyAsync(L.h_stats, L.stats, sizeof(SliceStats) * count, cudaMemcpyDeviceToHost, st));
         P3D_CUDA(cudaStreamSynchronize(st));
         for (int64_t i = 0; i < count; ++i) {
@@ -985,7 +1046,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             if (!L.h_stop[i]) {
                 P3D_REQUIRE(L.h_stats[i].n_cand > 0, P3D_ERR_NUMERIC,
                             "data-driven schedule: no coefficient between tau_min and tau_max in slice %lld", (long long)(first + i));
-                for (int k = 0; k < niter; ++k) tau[k] = cd(L.h_tau[i * niter + k].x, L.h_tau[i * niter + k].y);
+                for (int k = 0; k < niter; ++k) tau[k] = cd(L.h_tau64[i * niter + k].x, L.h_tau64[i * niter + k].y);
                 if (pr.sqrt_decay) apply_sqrt_decay(tau, false);
                 L.h_guard[i] = guard_of(L.h_stats[i]);
             }
@@ -1001,13 +1062,6 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     for (int64_t i = 0; i < count; ++i)
         if (L.h_stop[i] < 0)
             P3D_CUDA(cudaMemcpyAsync(OUT + i * ne, D + i * ne, sizeof(Cx<float>) * ne, cudaMemcpyDeviceToDevice, st));
-
-    // W was used as sort scratch (data-driven): redo the row pass
-    if (data_driven) {
-        BandArgs<float> B = A;
-        B.adaptive = 0; B.accum = 0;
-        for_list32(B, L.list, (int)count, [&](const BandArgs<float>& b, int nb) { launch_rows_init(P, L, b, nb); });
-    }
 
     // ---- phase 1: fp32 pilot over the slices still in fp32 -----------------------------------------------------------
     const bool guard_on = gfac > 0.0;
@@ -1118,6 +1172,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
                 rows64(B64, list1, n1r);
             }
             BandArgs<double> B64 = A64;
+            B64.adaptive = adaptive ? 1 : 0;
             int ptr = 0;
             int64_t its = 0;
             for (int kk = e64[0].first; kk < niter; ++kk) {

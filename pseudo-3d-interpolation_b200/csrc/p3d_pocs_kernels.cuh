@@ -293,7 +293,7 @@ __device__ __forceinline__ bool slice_stopped(int* stop, const double* S, int s,
 // generic column kernel.  MODE 0: statistics of X0 (optionally store X0), MODE 1: iterate
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int OP>
-__global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_constant__ AxisDev<T> ax1,
+__global__ void __launch_bounds__(512) k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_constant__ AxisDev<T> ax1,
                                const __grid_constant__ BandArgs<T> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int s = band_slice(A);
@@ -437,7 +437,7 @@ __global__ void k_cols_generic(const __grid_constant__ PocsGeom G, const __grid_
 // generic row kernel.  MODE 0: init (row FFT of d, nnz, sum|d|), MODE 1: iterate
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE>
-__global__ void k_rows_generic(const __grid_constant__ PocsGeom G, const __grid_constant__ AxisDev<T> ax2,
+__global__ void __launch_bounds__(512) k_rows_generic(const __grid_constant__ PocsGeom G, const __grid_constant__ AxisDev<T> ax2,
                                const __grid_constant__ BandArgs<T> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_s[32];

@@ -1,7 +1,11 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the reference's golden outputs
-and against the numpy oracle on seeded inputs.  Tolerance: relative L2 <= 1e-4 (fp32 device
-arithmetic vs the float64 reference, BASELINE.json north_star); observed traces exact at
-alpha = 1; iteration counts equal."""
+and against the numpy oracle on seeded inputs.  Tolerance: relative L2 <= 1e-4 (device result vs
+the float64 reference, BASELINE.json north_star) in the DEFAULT mode of the library (escalating
+precision: fp32 pilot, exact float64 restart); observed traces exact at
+alpha = 1; iteration counts equal.  Tests of the opt-in fp32-only mode say so and carry their own
+(looser, measured) bounds."""
+import multiprocessing as mp
+
 import numpy as np
 import pytest
 
@@ -27,6 +31,21 @@ def p3d():
     return m
 
 
+def _oracle_job(job):
+    x, mask, params = job
+    return orc.pocs_slice(x.astype(np.complex128), mask, **params).astype(np.complex64)
+
+
+def oracle_cube(d, fold, **params):
+    """float64 oracle over the slices of ``d``, one process per slice (full-size slices take 5 - 90 s each)."""
+    mask = orc.mask_from_fold(fold)
+    jobs = [(d[i], mask, params) for i in range(d.shape[0])]
+    if len(jobs) == 1:
+        return np.stack([_oracle_job(jobs[0])])
+    with mp.get_context("fork").Pool(min(len(jobs), mp.cpu_count())) as pool:
+        return np.stack(pool.map(_oracle_job, jobs, chunksize=1))
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_pocs_matches_reference_golden(case, golden, p3d):
     x, mask = make_input(case)
@@ -38,28 +57,13 @@ def test_pocs_matches_reference_golden(case, golden, p3d):
     ref = golden[f"{n}__y"]
     assert y.shape == ref.shape
     assert np.iscomplexobj(y) == np.iscomplexobj(ref)
-    nit_ref = int(golden[f"{n}__niterations"])
-    if case["params"]["eps"] > 0 and nit_ref < case["params"]["niter"]:
-        assert abs(info["niterations"] - nit_ref) <= 1      # fp32 cost may cross eps one iteration apart
+    assert info["niterations"] == int(golden[f"{n}__niterations"])
+    if case["params"]["thresh_op"].endswith("-percentile") and case["params"]["thresh_op"].startswith("hard"):
+        # the percentile operators run in fp32 only (a per-iteration order statistic of |X_k|): a coefficient within
+        # fp32 rounding of the percentile value may fall on either side of it
+        assert rel_l2(y, ref) <= 2e-3
     else:
-        assert info["niterations"] == nit_ref
-    if info["niterations"] == nit_ref:
-        # Tolerance 1e-4, except where the reference's own complex64 path already drifts more
-        # than that from its float64 result (hard threshold sinking into the noise floor,
-        # SURVEY 8a-C): there the bound is 3x that measured floor.
-        floor = float(golden[f"{n}__c64_drift"]) if f"{n}__c64_drift" in golden else 0.0
-        tol = RTOL if floor <= 0.3 * RTOL else 3.0 * floor
-        err = rel_l2(y, ref)
-        if case["params"]["thresh_op"] == "hard" and err > tol:
-            # The hard threshold is discontinuous: one coefficient whose |X| is within fp32
-            # rounding of tau_k may be kept by one fp32 implementation and killed by another
-            # (the reference's own complex64 path does this too, see *_c64_drift).  Such a
-            # single decision flip moves the result by about tau_k / ||X||, far below 1e-2 but
-            # above 1e-4.  Accept it only if it is that small and the run agrees closely
-            # everywhere else; test_hard_threshold_flip_statistics bounds how often it happens.
-            assert err <= 2e-3, err
-        else:
-            assert err <= tol, (err, floor)
+        assert rel_l2(y, ref) <= RTOL, rel_l2(y, ref)
     if case["params"]["alpha"] == 1.0 and not case.get("all_zero"):
         obs = mask == 1
         assert np.array_equal(np.asarray(y)[obs], x[obs])     # observed traces reproduced exactly
@@ -184,17 +188,17 @@ def test_early_exit_many_slices(p3d):
     y, info = plan.run(x, mask, **params)
     assert info["niterations"][2] == 0 and np.array_equal(y[2], x[2])
     for i in range(x.shape[0]):
-        assert abs(int(info["niterations"][i]) - nits[i]) <= 1, (i, info["niterations"][i], nits[i])
-        if int(info["niterations"][i]) == nits[i]:
-            assert rel_l2(y[i], refs[i]) <= RTOL
+        assert int(info["niterations"][i]) == nits[i], (i, info["niterations"][i], nits[i])
+        assert rel_l2(y[i], refs[i]) <= RTOL
 
 
-def test_hard_threshold_flip_statistics(p3d):
-    """fp32 hard thresholding: the GPU path must be as close to the float64 reference as the
+def test_fp32_only_mode_flip_statistics(p3d):
+    """precision = 32 (opt-in, fastest): fp32 hard thresholding must be as close to the float64 reference as the
     reference algorithm run in complex64 (numpy >= 2 keeps complex64) is -- same typical error,
-    and decision flips (error > 1e-4) not more frequent."""
+    and decision flips (error > 1e-4) not more frequent.  The default mode has no flips: next assertions."""
     params = dict(niter=20, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-4)
-    plan = p3d.PocsPlan(64, 64)
+    plan = p3d.PocsPlan(64, 64, precision=32)
+    auto = p3d.PocsPlan(64, 64)
     e_gpu, e_c64 = [], []
     for seed in range(300, 324):
         x, mask = make_input(dict(seed=seed, shape=(64, 64), keep=0.4, nwaves=4))
@@ -202,6 +206,8 @@ def test_hard_threshold_flip_statistics(p3d):
         e_c64.append(rel_l2(orc.pocs_slice(x, mask, **params), ref))
         y, _ = plan.run(x, mask, **params)
         e_gpu.append(rel_l2(y[0], ref))
+        ya, _ = auto.run(x, mask, **params)
+        assert rel_l2(ya[0], ref) <= 2e-7, (seed, rel_l2(ya[0], ref))        # default mode: one rounding to complex64
     e_gpu, e_c64 = np.array(e_gpu), np.array(e_c64)
     print("gpu   :", np.sort(e_gpu)[[0, 12, -3, -2, -1]], (e_gpu > RTOL).sum())
     print("np c64:", np.sort(e_c64)[[0, 12, -3, -2, -1]], (e_c64 > RTOL).sum())
@@ -211,23 +217,46 @@ def test_hard_threshold_flip_statistics(p3d):
 
 
 def test_full_size_config_slices(p3d):
-    """BASELINE configs 1 and 2 at their real slice sizes and iteration counts (noise-free
-    synthetic cube, hard / exponential, p_min = 1e-5).  In this regime the hard threshold sinks
-    into the dense leakage floor and fp32 arithmetic cannot hold 1e-4 against the float64
-    reference: the reference's own production path (complex64 under numpy >= 2) drifts
-    1e-4 .. 2e-3 from its float64 result.  The fp32 GPU path must therefore be
-    within max(1e-4, 2 x that drift); observed traces must be exact in any case."""
+    """BASELINE configs 1 and 2 at their real slice sizes, iteration counts and parameters (noise-free synthetic cube,
+    hard / exponential, p_min = 1e-5, eps = 0): <= 1e-4 against the float64 oracle in the default mode, observed traces
+    exact.  (fp32 alone is 1e-3 .. 3e-3 off here, and so is the reference's own complex64 path: SURVEY 8a-C.)"""
     from pseudo_3d_interpolation_b200 import synth
-    for cfg, ids in ((1, [20, 60, 100, 140, 200]), (2, [300])):
+    for cfg, ids in ((1, [20, 60, 100, 140, 200]), (2, [40, 300, 640, 1000])):
         d, fold, c = synth.sparse_freq_slices(cfg, slice_ids=ids)
         params = dict(niter=c["niter"], thresh_op=c["thresh_op"], thresh_model=c["thresh_model"], eps=0.0,
                       alpha=c["alpha"], p_max=0.99, p_min=1e-5)
-        y = p3d.pocs_cube(d, fold, **params)
-        ref = orc.pocs_cube(d, fold, upcast=True, **params)
-        c64 = orc.pocs_cube(d, fold, upcast=False, **params)
-        e_gpu, e_c64 = rel_l2(y, ref), rel_l2(c64, ref)
-        print(f"config {cfg}: cube rel-L2 vs float64 reference: gpu fp32 {e_gpu:.3e}, reference complex64 path {e_c64:.3e}")
-        assert e_gpu <= max(RTOL, 2.0 * e_c64), (e_gpu, e_c64)
+        res = {}
+        y = p3d.pocs_cube(d, fold, results=res, **params)
+        ref = oracle_cube(d, fold, **params)
+        e = rel_l2(y, ref)
+        print(f"config {cfg}: cube rel-L2 vs float64 oracle {e:.3e}; per slice {[float('%.1e' % rel_l2(y[i], ref[i])) for i in range(len(ids))]}")
+        assert e <= RTOL, e
+        for i in range(len(ids)):
+            assert rel_l2(y[i], ref[i]) <= RTOL, (cfg, ids[i], rel_l2(y[i], ref[i]))
+        assert np.all(res["niterations"] == c["niter"])
+        obs = orc.mask_from_fold(fold) == 1
+        assert np.array_equal(y[:, obs], d[:, obs])
+
+
+@pytest.mark.parametrize("cfg,ids", [(3, [700]), (4, [1200]), (5, [30, 200, 500])])
+def test_full_size_config_slices_c3_c4_c5(cfg, ids, p3d):
+    """BASELINE configs 3 (1201 x 847, soft / linear, 100 iterations), 4 (2000 x 2000, hard / data-driven, alpha = 0.7,
+    100 iterations, line-pattern fold with fold = 2 crossings) and 5 (256 x 256, garrote / exponential, 30 iterations) at
+    their real sizes and parameters (p_min = 1e-5, eps = 0) against the float64 oracle: <= 1e-4."""
+    from pseudo_3d_interpolation_b200 import synth
+    d, fold, c = synth.sparse_freq_slices(cfg, slice_ids=ids)
+    assert (fold.max() == 2) == (cfg == 4)
+    params = dict(niter=c["niter"], thresh_op=c["thresh_op"], thresh_model=c["thresh_model"], eps=0.0,
+                  alpha=c["alpha"], p_max=0.99, p_min=1e-5)
+    res = {}
+    y = p3d.pocs_cube(d, fold, results=res, **params)
+    ref = oracle_cube(d, fold, **params)
+    for i in range(len(ids)):
+        e = rel_l2(y[i], ref[i])
+        print(f"config {cfg} slice {ids[i]}: rel-L2 vs float64 oracle {e:.3e}")
+        assert e <= RTOL, (cfg, ids[i], e)
+    assert np.all(res["niterations"] == c["niter"])
+    if c["alpha"] == 1.0:
         obs = orc.mask_from_fold(fold) == 1
         assert np.array_equal(y[:, obs], d[:, obs])
 
@@ -256,19 +285,18 @@ def test_full_size_properties_all_configs(cfg, ids, niter, p3d):
     assert np.abs(y[:, ~obs]).max() > 0
 
 
-def test_full_size_config_slices_soft_fp32(p3d):
-    """Soft operator, same slices, fp32 path.  With the reference's complex tau (Q1) even the
-    soft and garrote operators jump at |X| = Re(tau): just below the factor is clipped to 0, at
-    it the factor is -i Im(tau)/|X| != 0.  fp32 rounding can therefore flip single coefficients
-    exactly as for the hard operator, and the bound here is the flip bound (2e-3), not 1e-4; the
-    float64 state mode (next test) holds 1e-4 on the same input."""
+def test_full_size_config_slices_soft(p3d):
+    """Soft operator on config-1 slices at full size.  With the reference's complex tau (Q1) even the soft and garrote
+    operators jump at a threshold modulus (below it the factor is clipped to 0, at it the factor is -i Im(tau)/|X|), so
+    fp32 alone flips single coefficients here too (2e-4 measured); the default mode holds 1e-4."""
     from pseudo_3d_interpolation_b200 import synth
     d, fold, c = synth.sparse_freq_slices(1, slice_ids=[20, 100, 200])
-    params = dict(niter=c["niter"], thresh_op="soft", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-5)
-    y = p3d.pocs_cube(d, fold, **params)
-    ref = orc.pocs_cube(d, fold, **params)
-    print(f"soft fp32 full size: rel-L2 {rel_l2(y, ref):.3e}")
-    assert rel_l2(y, ref) <= 2e-3
+    for op in ("soft", "garrote"):
+        params = dict(niter=c["niter"], thresh_op=op, thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-5)
+        y = p3d.pocs_cube(d, fold, **params)
+        ref = oracle_cube(d, fold, **params)
+        print(f"{op} full size: rel-L2 {rel_l2(y, ref):.3e}")
+        assert rel_l2(y, ref) <= RTOL
 
 
 # ------------------------------------------------------------------------------------------------
@@ -398,25 +426,12 @@ def test_config3_plans_match_generic_and_oracle(shape, op, model, alpha, version
     gen.set_option("force_generic", 1)
     yg, infog = gen.run(x, mask, version=version, want_costs=True, **params)
     assert list(info["niterations"]) == list(infog["niterations"])
-    tol = RTOL if op != "hard" else 1e-2     # hard + data-driven: thresholds walk through the dense coefficient population
-    # two fp32 implementations may decide one coefficient at a threshold jump differently (here it is the generic
-    # path that flips one at garrote / adaptive / (1201, 48), 2.2e-3 off the oracle; tools/diag_c3.py): loose bound
-    assert rel_l2(y, yg) <= max(5e-3, tol), rel_l2(y, yg)
+    assert rel_l2(y, yg) <= RTOL, rel_l2(y, yg)
     for i in range(2):
         oinfo = {}
         ref = orc.pocs_slice(x[i].astype(np.complex128), mask, version=version, info=oinfo, **params)
-        # with eps > 0 the stop decision (cost < eps, fp32 sums) may fall one iteration apart from the float64
-        # oracle's, and a complex tau makes even the soft operator jump at |X| = Re(tau): flip bound there
-        t = tol if (eps == 0.0 and oinfo["niterations"] == info["niterations"][i]) else max(tol, 2e-3)
-        err = rel_l2(y[i], ref)
-        if err > t and eps == 0.0:
-            # a coefficient on the other side of a threshold jump in fp32 (garrote / adaptive at (48, 1201): 3e-7 up to
-            # iteration 6, 4.7e-4 at iteration 7 for the register AND the generic kernels, tools/diag_c3_rows.py):
-            # accepted only if it is that small and the float64 state mode reproduces the oracle on the same input
-            y64, _ = p3d.PocsPlan(*shape, precision=64).run(x[i:i + 1], mask, version=version, **params)
-            assert rel_l2(y64[0], ref) <= 2e-7 and err <= 2e-3, (i, err, rel_l2(y64[0], ref))
-        else:
-            assert err <= t, (i, err, oinfo["niterations"], info["niterations"][i])
+        assert oinfo["niterations"] == info["niterations"][i]
+        assert rel_l2(y[i], ref) <= RTOL, (i, rel_l2(y[i], ref))
     if alpha == 1.0 and version == "regular":
         obs = mask == 1
         assert np.array_equal(y[:, obs], x[:, obs])
@@ -441,16 +456,14 @@ def test_more_register_plans_match_oracle(n, p3d):
         y, info = plan.run(x, mask, **params)
         for i in range(2):
             ref = orc.pocs_slice(x[i].astype(np.complex128), mask, **params)
-            # 3e-4: with the reference's complex tau the soft operator jumps at |X| = Re(tau), one coefficient on the
-            # other side of it costs about 1e-4 here (seen at (20, 768): 1.2e-4); a wrong transform costs O(1)
-            assert rel_l2(y[i], ref) <= 3e-4, (shape, i, rel_l2(y[i], ref))
+            assert rel_l2(y[i], ref) <= RTOL, (shape, i, rel_l2(y[i], ref))
     # square slice of this size: both axes on register plans, hard threshold, observed traces exact
     if n <= 1024:
         x, mask = make_input(dict(seed=n + 1, shape=(n, n), keep=0.25, nwaves=5))
         params = dict(niter=4, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-2)
         y, _ = p3d.PocsPlan(n, n).run(x.astype(np.complex64), mask, **params)
         ref = orc.pocs_slice(x.astype(np.complex128), mask, **params)
-        assert rel_l2(y[0], ref) <= 2e-3
+        assert rel_l2(y[0], ref) <= RTOL
         assert np.array_equal(y[0][mask == 1], x.astype(np.complex64)[mask == 1])
 
 
@@ -631,9 +644,8 @@ def test_edge_many_small_cubes_with_own_masks_and_early_exit(p3d):
     for i in range(x.shape[0]):
         oi = {}
         ref = orc.pocs_slice(x[i].astype(np.complex128), mask[i // per], info=oi, **params)
-        assert abs(int(info["niterations"][i]) - oi["niterations"]) <= 1
-        if int(info["niterations"][i]) == oi["niterations"]:
-            assert rel_l2(y[i], ref) <= RTOL, (i, rel_l2(y[i], ref))
+        assert int(info["niterations"][i]) == oi["niterations"], (i, info["niterations"][i], oi["niterations"])
+        assert rel_l2(y[i], ref) <= RTOL, (i, rel_l2(y[i], ref))
 
 
 @pytest.mark.gpu

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.p3d_abi_version() == 2
+    assert lib.p3d_abi_version() == 3
 
 
 def test_params_struct_layout_matches_header():
