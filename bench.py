@@ -28,8 +28,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-B_ALG_PER_ELEM = 73.0          # 4 streaming passes x 16 B + 8 B observed data + 1 B mask
-KERNEL_BYTES_PER_ELEM = {"cols_iter": 32.0, "rows_iter": 41.0}
+B_ALG_PER_ELEM = 73.0          # SURVEY 8d contract model: 4 streaming passes x 16 B + 8 B observed data + 1 B mask (complex64 state)
+# bytes the FUSED kernels have to move per element and launch (the floor their DRAM traffic is compared with):
+# complex64 state: column pass 8 + 8, row pass 8 + 8 + 8 (observed data) + 1/8 (packed mask);
+# complex128 state (escalating / float64 modes): 16 + 16 and 16 + 16 + 8 + 1/8
+KERNEL_BYTES_PER_ELEM = {"cols_iter": 16.0, "rows_iter": 24.125, "cols_iter64": 32.0, "rows_iter64": 40.125}
+FUSED_FLOOR_32 = 40.125
+FUSED_FLOOR_64 = 72.125
 
 
 def parse_args():
@@ -46,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-diag", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precision", default="auto", choices=["auto", "32", "64"],
+                    help="auto = escalating fp32 -> complex128 (default, within 1e-4 of the float64 reference); 32 = fp32 only; 64 = complex128 throughout")
+    ap.add_argument("--e2e-slices", type=int, default=0, help="slices per GPU per end-to-end step (0 = all at 1-2 GPUs, 512 beyond: pinned host memory)")
     return ap.parse_args()
 
 
@@ -205,7 +213,7 @@ def main():
         if rank != 0:
             return 0
         procs = min(os.cpu_count() or 1, 64)
-        it_cpu = min(niter, cpu_niter_for_budget(c, procs, 12.0))
+        it_cpu = niter                                   # the configuration's own iteration count (same_config)
         vals = []
         for i in range(args.warmup + args.steps):
             v, wall, its = cpu_sample(args.config, c, it_cpu, procs, procs)
@@ -257,7 +265,8 @@ def main():
     x_dev, mask_dev = synth_device(torch, dev, args.config, c, rank * ns, ns, nf_full)
     out_dev = torch.empty_like(x_dev)
     torch.cuda.synchronize()
-    plan = p3d.PocsPlan(n1, n2, device=local)
+    precision = {"auto": 0, "32": 32, "64": 64}[args.precision]
+    plan = p3d.PocsPlan(n1, n2, device=local, precision=precision)
     if args.band >= 0:
         plan.set_option("band_slices", args.band)
     desc = plan.describe()
@@ -292,6 +301,8 @@ def main():
     plan.set_profiling(False)
     slice_its = int(nit.sum())                          # per step, this rank
     assert slice_its == ns * niter, (slice_its, ns * niter)
+    esc_slices, esc_its = plan.escalation() if precision == 0 else ((ns, ns * niter) if precision == 64 else (0, 0))
+    f64_share = esc_its / max(1, ns * niter)            # share of the slice-iterations that ran on complex128 state
 
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     tot_its = torch.tensor([float(slice_its)], dtype=torch.float64, device=dev)
@@ -302,12 +313,44 @@ def main():
     total_its_per_step = float(tot_its[0])
     value = total_its_per_step * args.steps / (dev_ms_max * 1e-3)
 
+    # ---- strong scaling (N > 1): ONE cube of nf_full slices split into contiguous frequency bands, one band per GPU
+    strong = None
+    if world > 1:
+        from pseudo_3d_interpolation_b200.pocs import band_bounds
+        lo, hi = band_bounds(nf_full, world)[rank]
+        ns_s = hi - lo
+        if ns_s <= ns:
+            nit_s = np.zeros(max(ns_s, 1), np.int32)
+
+            def step_strong():
+                if ns_s > 0:
+                    plan.run_device(x_dev.data_ptr(), mask_dev.data_ptr(), out_dev.data_ptr(), ns_s, params, nit=nit_s)
+
+            step_strong()
+            barrier()
+            plan.event_record(4)
+            for _ in range(args.steps):
+                step_strong()
+            plan.event_record(5)
+            s_ms = plan.event_elapsed_ms(4, 5)
+            barrier()
+            ts = torch.tensor([s_ms], dtype=torch.float64, device=dev)
+            tn = torch.tensor([float(nit_s[:ns_s].sum())], dtype=torch.float64, device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+            strong = {"value": float(tn[0]) * args.steps / (float(ts[0]) * 1e-3), "unit": "slice-iterations/s", "scaling": "strong",
+                      "cube_slices": nf_full, "slices_per_gpu": -(-nf_full // world), "ms_per_step": float(ts[0]) / args.steps,
+                      "what": "one cube of nf_full rfft slices split into contiguous bands (pocs.band_bounds), device-resident, max over ranks"}
+        else:
+            strong = {"skipped": f"a band of the cube ({ns_s} slices) exceeds the {ns} slices resident per GPU; rerun with --slices {ns_s}"}
+
     # ---- end to end: pinned host buffers in, pinned host buffers out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
         # bounded pinned footprint: at most 512 slices per rank per e2e step (the chunk pipeline
         # of p3d_pocs_run is in steady state long before that), so 8 ranks stay below 70 GB pinned
-        ns_e = min(ns, 512)
+        ns_e = args.e2e_slices if args.e2e_slices > 0 else (ns if world <= 2 else min(ns, 512))
+        ns_e = min(ns_e, ns)
         hx = _lib.PinnedArray((ns_e, n1, n2), np.complex64)
         ho = _lib.PinnedArray((ns_e, n1, n2), np.complex64)
         hm = _lib.PinnedArray((n1, n2), np.uint8)
@@ -356,9 +399,12 @@ def main():
     dom = max(KERNEL_BYTES_PER_ELEM, key=lambda k: prof[k]["ms"])
     launches = prof[dom]["launches"]
     avg_ms = prof[dom]["ms"] / max(launches, 1)
-    slices_per_launch = ns * args.steps * niter / max(launches, 1)
+    # slices per launch of the dominant kernel: the complex128 kernels run over the slices already switched
+    if dom.endswith("64"):
+        slices_per_launch = esc_its * args.steps / max(launches, 1) if precision == 0 else ns * args.steps * niter / max(launches, 1)
+    else:
+        slices_per_launch = (ns * niter - (esc_its if precision == 0 else 0)) * args.steps / max(launches, 1)
     alg_bytes = KERNEL_BYTES_PER_ELEM[dom] * n1 * n2 * slices_per_launch
-    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -367,20 +413,28 @@ def main():
             traffic = tj["dram_bytes_per_slice"] * slices_per_launch if (tj and n1 == 1000 and n2 == 1000) else None
         except Exception:
             traffic = None
+    moved = traffic if traffic else alg_bytes
+    achieved = moved / (avg_ms * 1e-3) / 1e9
+    floor_per_it = (FUSED_FLOOR_32 * (1.0 - f64_share) + FUSED_FLOOR_64 * f64_share) * n1 * n2
+    rate1 = value / world
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                # DRAM bytes actually moved (ncu) over the same launch time: the fused kernels move less than the
-                # four-pass model counts (the row kernel writes the result only in the last iteration), so `frac` may
-                # exceed 1 while DRAM itself is not saturated
-                "dram_achieved_GBps": (traffic / (avg_ms * 1e-3) / 1e9) if traffic else None,
-                "note": "achieved = SURVEY 8(d) model bytes (73 B/element/iteration, split 32 cols + 41 rows) / measured launch time",
-                "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
-                "whole_iteration": {"alg_bytes_per_slice_iteration": B_ALG_PER_ELEM * n1 * n2,
-                                    "achieved_GBps": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9,
-                                    "frac_of_measured_peak": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9 / peak,
-                                    "frac_of_8TBps_nominal": value / world * B_ALG_PER_ELEM * n1 * n2 / 1e9 / 8000.0},
+                "note": ("achieved = DRAM bytes the dominant kernel moves per launch (ncu dram__bytes_read + write, profiles/traffic.json; the "
+                         "algorithmic bytes of the fused kernel when no capture exists for this shape) / its average launch time (CUDA events)"),
+                "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "slices_per_launch": slices_per_launch,
+                "complex128_share_of_slice_iterations": f64_share, "slices_switched_to_complex128": esc_slices,
+                "whole_iteration": {
+                    # what one slice-iteration has to move with the fused two-kernel structure (16 + 24 B per element in complex64,
+                    # 32 + 40 B in complex128, weighted by the measured share of complex128 slice-iterations)
+                    "fused_floor_bytes_per_slice_iteration": floor_per_it,
+                    "frac_of_fused_floor": rate1 * floor_per_it / 1e9 / peak,
+                    # the SURVEY 8(d) contract model (four streaming passes, complex64): 73 B per element and slice-iteration
+                    "contract_73B_bytes_per_slice_iteration": B_ALG_PER_ELEM * n1 * n2,
+                    "contract_73B_achieved_GBps": rate1 * B_ALG_PER_ELEM * n1 * n2 / 1e9,
+                    "contract_73B_frac_of_measured_peak": rate1 * B_ALG_PER_ELEM * n1 * n2 / 1e9 / peak,
+                    "contract_73B_frac_of_8TBps_nominal": rate1 * B_ALG_PER_ELEM * n1 * n2 / 1e9 / 8000.0},
                 # FFT flop rate, 5 N log2 N convention: two 2-D transforms + ~30 flops of element-wise work per element
-                "fft_tflops": value / world * (2 * 5 * n1 * n2 * math.log2(n1 * n2) + 30.0 * n1 * n2) / 1e12,
+                "fft_tflops": rate1 * (2 * 5 * n1 * n2 * math.log2(n1 * n2) + 30.0 * n1 * n2) / 1e12,
                 "kernel_share_of_step": {k: prof[k]["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())) for k in prof if prof[k]["launches"]}}
     gpu_launches = int(sum(v["launches"] for v in prof.values()))
 
@@ -416,20 +470,25 @@ def main():
     if not args.no_diag:
         extras = {}
         try:
-            ns64 = min(64, ns)
-            x64 = torch.randn((ns64, n1, n2), dtype=torch.complex64, device=dev) * mask_dev[None]
-            o64 = torch.empty_like(x64)
-            p64 = p3d.PocsPlan(n1, n2, device=local, precision=64)
-            par64 = p3d.make_params(niter=20, thresh_op=c["thresh_op"], thresh_model="exponential", eps=0.0, alpha=c["alpha"])
-            p64.run_device(x64.data_ptr(), mask_dev.data_ptr(), o64.data_ptr(), ns64, par64)
-            p64.event_record(0)
-            p64.run_device(x64.data_ptr(), mask_dev.data_ptr(), o64.data_ptr(), ns64, par64)
-            p64.event_record(1)
-            extras["float64_state_mode"] = {"value": ns64 * 20 / (p64.event_elapsed_ms(0, 1) * 1e-3), "unit": "slice-iterations/s",
-                                            "sample": f"{ns64} slices x 20 iterations, precision=64", "plan": p64.describe().split("precision=64; ")[-1]}
-            p64.close(); del x64, o64
+            # the two other precision modes on a sample of the same synthetic cube (device-resident)
+            nsx = min(128, ns)
+            xs, ms_ = synth_device(torch, dev, args.config, c, 300, nsx, nf_full)
+            os_ = torch.empty_like(xs)
+            for name, prec in (("fp32_only_mode", 32), ("float64_state_mode", 64), ("escalating_mode", 0)):
+                if prec == precision:
+                    continue
+                px = p3d.PocsPlan(n1, n2, device=local, precision=prec)
+                px.run_device(xs.data_ptr(), ms_.data_ptr(), os_.data_ptr(), nsx, params)
+                px.event_record(0)
+                px.run_device(xs.data_ptr(), ms_.data_ptr(), os_.data_ptr(), nsx, params)
+                px.event_record(1)
+                extras[name] = {"value": nsx * niter / (px.event_elapsed_ms(0, 1) * 1e-3), "unit": "slice-iterations/s",
+                                "sample": f"{nsx} slices x {niter} iterations of the synthetic cube, precision={prec or 'auto'}",
+                                "plan": px.describe().split("precision=")[-1]}
+                px.close()
+            del xs, os_
         except Exception as ex:          # noqa: BLE001
-            extras["float64_state_mode"] = {"error": str(ex)[:200]}
+            extras["precision_modes"] = {"error": str(ex)[:200]}
         try:
             nsf = min(128, ns)
             xf = torch.randn((nsf, n1, n2), dtype=torch.complex64, device=dev)
@@ -481,11 +540,12 @@ def main():
 
     line = {"metric": "pocs_slice_iterations_per_s", "value": value, "unit": "slice-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c64 (fp32 complex)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {0: "c64 -> c128 (fp32 pilot, complex128 state after the exact restart)", 32: "c64 (fp32 complex)", 64: "c128"}[precision], "data": "synthetic",
             "config": {"workload": cfg_workload, "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2" % (ns * n1 * n2 * 8 / 1e9),
-                       "plan": desc, "host": numa + f"; {os.cpu_count()} cpus", "timing": "CUDA events on the library stream, max over ranks",
+                       "precision": args.precision, "plan": desc, "host": numa + f"; {os.cpu_count()} cpus", "timing": "CUDA events on the library stream, max over ranks",
                        "wall_ms_per_step": wall_ms_max / args.steps},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "strong": strong, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
             "diag_cufft_chain": diag, "extras": extras, "checksum": checksum}
     emit(line)
     if dist is not None:
