@@ -414,7 +414,7 @@ def main():
         except Exception:
             traffic = None
     moved = traffic if traffic else alg_bytes
-    achieved = moved / (avg_ms * 1e-3) / 1e9
+    achieved = moved / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     floor_per_it = (FUSED_FLOOR_32 * (1.0 - f64_share) + FUSED_FLOOR_64 * f64_share) * n1 * n2
     rate1 = value / world
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -30,6 +30,12 @@ __device__ __forceinline__ void mix_twiddle(Cx<T> (&x)[R], const Cx<T>* __restri
             if (r2 > 0) x[2 * r2] = (DIR < 0) ? cmul(x[2 * r2], cmake<T>(w.x, w.y)) : cmulc(x[2 * r2], cmake<T>(w.x, w.y));
             x[2 * r2 + 1] = (DIR < 0) ? cmul(x[2 * r2 + 1], cmake<T>(w.z, w.w)) : cmulc(x[2 * r2 + 1], cmake<T>(w.z, w.w));
         }
+    } else if constexpr (sizeof(T) == 8 && (R > 3)) {
+        // complex128: powers of W^k instead of R - 1 table loads (see twiddle_powers)
+        Cx<double> w[R];
+        twiddle_powers<R>(tab[tw_index(R, Ns, 1, 0) + k * (R % 2 == 0 ? 2 : 1)], w);
+#pragma unroll
+        for (int r = 1; r < R; ++r) x[r] = (DIR < 0) ? cmul(x[r], w[r]) : cmulc(x[r], w[r]);
     } else {
 #pragma unroll
         for (int r = 1; r < R; ++r) {
@@ -50,6 +56,7 @@ template <int N_, int Ra, int Rb> struct MixPlan3 {
     static constexpr int D2 = exch_delta(Ra, Rb);           // padding after every block of Ra*Rb positions (exchange 2)
     static constexpr int NB2 = Ra * Ra;                     // butterflies of the middle pass
     static constexpr int Q2 = (NB2 + T - 1) / T;            // rounds of the middle pass per thread
+    static constexpr bool SINGLE_BUFFER_OK = (Q2 == 1);     // see pass 2
     static constexpr int LINE_RAW = (N + (N / Ra - 1) * D1) > (N + (N / T - 1) * D2) ? (N + (N / Ra - 1) * D1) : (N + (N / T - 1) * D2);
     static constexpr int LINE = (LINE_RAW + 1 + 3) & ~3;
     static void radices(int* out) { out[0] = Ra; out[1] = Rb; out[2] = Ra; }
@@ -67,7 +74,29 @@ template <int N_, int Ra, int Rb> struct MixPlan3 {
         }
         acc.sync();
         // ---- pass 2: radix Rb, Ns = Ra; inputs b + r*Ra*Ra, outputs hi*(Ra*Rb) + r*Ra + k
-        {
+        if constexpr (Q2 == 1) {
+            // one round: operands in registers before anything is written, so a single exchange buffer works as well
+            // (acc.pre_sync() is the barrier between the reads and the writes there, a no-op with two buffers)
+            const Cx<F>* in = acc.line(BUF0);
+            Cx<F>* out = acc.line(BUF0 ^ 1);
+            const int b = j;
+            const bool act = (T <= NB2) || (b < NB2);
+            const int hi = b / Ra, k = b - hi * Ra;
+            Cx<F> x[Rb];
+            if (act) {
+                const Cx<F>* rd = in + (b + hi * D1) * S;
+#pragma unroll
+                for (int r = 0; r < Rb; ++r) x[r] = rd[(r * (Ra * Ra + Ra * D1)) * S];
+                mix_twiddle<DIR, Rb, Ra, F>(x, tw, k);
+                Bfly<Rb, DIR, F>::run(x);
+            }
+            acc.pre_sync();
+            if (act) {
+                Cx<F>* wr = out + (hi * (T + D2) + k) * S;
+#pragma unroll
+                for (int r = 0; r < Rb; ++r) wr[(r * Ra) * S] = x[r];
+            }
+        } else {
             const Cx<F>* in = acc.line(BUF0);
             Cx<F>* out = acc.line(BUF0 ^ 1);
 #pragma unroll

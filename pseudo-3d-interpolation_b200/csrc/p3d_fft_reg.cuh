@@ -64,6 +64,20 @@ template <int... Rs> struct PaddedLine {
 __host__ __device__ constexpr int tw_index(int R, int Ns, int r, int k) {
     return (R % 2 == 0) ? (((r >> 1) * Ns + k) * 2 + (r & 1)) : (r * Ns + k);
 }
+// complex128 twiddles: W^{r k}, r = 2 .. R-1, from W^k alone (squares and products, depth <= 4).  The L1 / shared-memory
+// data pipe is the busiest unit of the complex128 kernels (ncu: 80 % in the row kernel) and R - 1 16-byte table loads per
+// butterfly were a quarter of its wavefronts; the FP64 pipe has the headroom for the 3 - 4 extra instructions per factor.
+template <int R>
+__device__ __forceinline__ void twiddle_powers(const Cx<double> w1, Cx<double> (&w)[R]) {
+    w[0] = cmake<double>(1.0, 0.0);
+    w[1] = w1;
+#pragma unroll
+    for (int r = 2; r < R; ++r) {
+        if (r % 2 == 0) { const Cx<double> h = w[r / 2]; w[r] = cmake<double>(h.x * h.x - h.y * h.y, 2.0 * h.x * h.y); }
+        else w[r] = cmul(w[(r + 1) / 2], w[r / 2]);
+    }
+}
+
 template <int N, int E, int DIR, int Ns, int BUF, int TWOFF, typename T, typename Acc, int... Rs> struct RegPasses;
 
 template <int N, int E, int DIR, int Ns, int BUF, int TWOFF, typename T, typename Acc>
@@ -109,6 +123,12 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
                         if (r2 > 0) x[2 * r2] = (DIR < 0) ? cmul(x[2 * r2], cmake<T>(w.x, w.y)) : cmulc(x[2 * r2], cmake<T>(w.x, w.y));
                         x[2 * r2 + 1] = (DIR < 0) ? cmul(x[2 * r2 + 1], cmake<T>(w.z, w.w)) : cmulc(x[2 * r2 + 1], cmake<T>(w.z, w.w));
                     }
+                } else if constexpr (sizeof(T) == 8 && (R > 3)) {
+                    const Cx<T>* tp = tw + TWOFF;
+                    Cx<double> w[R];
+                    twiddle_powers<R>(tp[tw_index(R, Ns, 1, 0) + k * (R % 2 == 0 ? 2 : 1)], w);
+#pragma unroll
+                    for (int r = 1; r < R; ++r) x[r] = (DIR < 0) ? cmul(x[r], w[r]) : cmulc(x[r], w[r]);
                 } else {
                     const Cx<T>* tp = tw + TWOFF;
 #pragma unroll

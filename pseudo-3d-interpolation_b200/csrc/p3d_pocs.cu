@@ -72,6 +72,8 @@ struct p3d_plan {
     double guard_factor = 1024.0;    // guard half-width in units of eps32 * rms|X| (escalating mode)
     int seg_iters = 4;               // escalating mode: iterations between two compactions of the active-slice list
     int arena_cap = 16384;           // escalating mode: support-record entries per slice (all pilot iterations together)
+    int support_cap = 0;             // escalating mode: largest support replayed per iteration (0 = 4 sqrt(n1 n2): where one more
+                                     // replayed iteration, ~|S|^2 gathers, costs what the complex128 iteration it replaces does)
     Cx<double>* mhat = nullptr; int64_t mhat_masks = 0;          // fft2 of the mask planes in complex128 (exact restart)
     Cx<float>* mask_c64 = nullptr; SliceStats* mh_stats = nullptr; double2* mh_cand = nullptr; int mh_cand_stride = 0;
     int64_t n_escalated = 0, n_esc_iters = 0;   // statistics of the last run (escalating mode)
@@ -812,7 +814,26 @@ k_replay(const int i, const int* __restrict__ list, const int* __restrict__ esc,
         if ((int)threadIdx.x < nq) { sp[threadIdx.x] = ar[p0 + q0 + threadIdx.x]; sy[threadIdx.x] = yv[p0 + q0 + threadIdx.x]; }
         __syncthreads();
         if (valid) {
-            for (int q = 0; q < nq; ++q) {
+            // eight gathers in flight per thread (the mhat plane lives in L2: latency, not bandwidth, bounds this loop)
+            int q = 0;
+            for (; q + 8 <= nq; q += 8) {
+                double2 m[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned ps = sp[q + u];
+                    int dr = jr - (int)(ps >> 16); if (dr < 0) dr += n1;
+                    int dc = jc - (int)(ps & 0xffffu); if (dc < 0) dc += n2;
+                    m[u] = __ldg(reinterpret_cast<const double2*>(mh) + (long long)dr * n2 + dc);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double2 ys = sy[q + u];
+                    if (sp[q + u] == pj) { selfx = ys.x; selfy = ys.y; }
+                    accx += m[u].x * ys.x - m[u].y * ys.y;
+                    accy += m[u].x * ys.y + m[u].y * ys.x;
+                }
+            }
+            for (; q < nq; ++q) {
                 const unsigned ps = sp[q];
                 const double2 ys = sy[q];
                 if (ps == pj) { selfx = ys.x; selfy = ys.y; }
@@ -1075,14 +1096,19 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     };
     upload_list(active);
     const bool need_sync = guard_on || pr.eps > 0.0;
-    const int seg = std::max(1, P->seg_iters);
+    // iterations between two compactions: at least seg_iters, and enough work (~2 ms) that the wait is amortised
+    const double est_iter_ms = 12e-9 * (double)ne * (double)count;       // ~12 ns per 1000 elements and fp32 iteration
+    const int seg = std::max(std::max(1, P->seg_iters), (int)std::min(16.0, std::ceil(2.0 / std::max(est_iter_ms, 1e-6))));
     int k = 0;
     while (k < niter && !active.empty()) {
         const int kend = need_sync ? std::min(niter, k + (k == 0 && guard_on ? 1 : seg)) : niter;
         for (; k < kend; ++k) {
             BandArgs<float> B = A;
             B.guard = guard_on ? L.guard : nullptr;
-            if (guard_on) { B.arena = L.arena; B.acnt = L.acnt; B.astart = L.astart; B.arena_cap = acap; }
+            if (guard_on) {
+                B.arena = L.arena; B.acnt = L.acnt; B.astart = L.astart; B.arena_cap = acap;
+                B.scap = P->support_cap > 0 ? P->support_cap : (int)(4.0 * std::sqrt((double)ne));
+            }
             B.k = k; B.last = (k == niter - 1) ? 1 : 0;
             B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
             for_list32(B, L.list, (int)active.size(), [&](const BandArgs<float>& b, int nb) {
@@ -1580,6 +1606,7 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     }
     else if (!strcmp(key, "guard_factor")) P->guard_factor = (double)value;
     else if (!strcmp(key, "seg_iters")) P->seg_iters = (int)std::max<int64_t>(1, value);
+    else if (!strcmp(key, "support_cap")) P->support_cap = (int)std::max<int64_t>(0, value);
     else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(128, value));
     else if (!strcmp(key, "spec_variant")) {
         try { DeviceGuard g(P->device); install_spec(P, (int)value); } catch (const P3dFail& f) { return f.code; }

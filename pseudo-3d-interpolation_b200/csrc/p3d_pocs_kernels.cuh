@@ -104,6 +104,7 @@ template <typename T> struct BandArgs {
     int* acnt;                   // [band] entries used
     int* astart;                 // [band][niter + 1] first entry of iteration k (astart[.][0] = 0)
     int arena_cap;
+    int scap;                    // freeze the slice after an iteration that kept more than scap coefficients (replay cost ~ |S|^2)
     int restart;                 // complex128 kernels: this launch rebuilds x_{k_e - 1} (iteration index = esc[s] - 2 per slice)
     int store_x0_inplace;        // complex128 statistics kernel: leave X0 in W
 };
@@ -122,6 +123,14 @@ template <typename T> __device__ __forceinline__ bool slice_escalated(const Band
     if (sizeof(T) != 4 || !A.esc) return false;
     const int e = A.esc[s];
     return e != 0 && e <= A.k;
+}
+// fp32 row kernels, one thread per slice and iteration: close this iteration's support record; a support that has
+// outgrown the sparse replay freezes the slice from the NEXT iteration on (its own record is complete)
+template <typename T> __device__ __forceinline__ void close_support_record(const BandArgs<T>& A, const int s) {
+    const int end = A.acnt[s];
+    int* as = A.astart + (long long)s * (A.niter + 1) + A.k;
+    as[1] = end;
+    if (A.scap > 0 && end - as[0] > A.scap && A.esc[s] == 0) A.esc[s] = A.k + 2;
 }
 // fp32 row kernels: esc = k + 1 was set by the column pass of this iteration k (or earlier): complex128 redoes iteration k
 template <typename T> __device__ __forceinline__ bool slice_frozen(const BandArgs<T>& A, const int s) {
@@ -448,8 +457,7 @@ __global__ void __launch_bounds__(512) k_rows_generic(const __grid_constant__ Po
     if (MODE == 0 && A.adaptive) { if (A.stop[s] != 0) return; }
     // complex128 restart launch: the iteration rebuilt is the one before the slice's switch
     const int kk = (MODE == 1 && A.restart) ? A.esc[s] - 2 : A.k;
-    if (MODE == 1 && sizeof(T) == 4 && A.astart && blockIdx.x == 0 && tid == 0)
-        A.astart[(long long)s * (A.niter + 1) + A.k + 1] = A.acnt[s];      // end of this iteration's support record
+    if (MODE == 1 && sizeof(T) == 4 && A.astart && blockIdx.x == 0 && tid == 0) close_support_record(A, s);
 
     const int r0 = blockIdx.x * G.RB;
     const int nr = min(G.RB, G.n1 - r0);

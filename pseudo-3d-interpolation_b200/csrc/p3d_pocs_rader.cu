@@ -298,7 +298,7 @@ k_rows_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     Cx<float>* dst = reinterpret_cast<Cx<float>*>(smem_raw) + 2 * MP::LINE;   // observed row, natural order
     for (int i = j; i < P; i += T) { land[i] = Wp[i]; dst[i] = Dp[i]; }
     if (stopped != 0 || slice_frozen(A, s)) return;
-    if (A.astart && row == 0 && j == 0) A.astart[(long long)s * (A.niter + 1) + A.k + 1] = A.acnt[s];
+    if (A.astart && row == 0 && j == 0) close_support_record(A, s);
     __syncthreads();
 
     Cx<float> v[E];

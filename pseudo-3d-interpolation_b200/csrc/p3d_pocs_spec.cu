@@ -123,6 +123,7 @@ SpecKernels select_spec_kernels(int n_iline, int n_xline, int variant) {
 
 // ---- float64 state mode: the same iteration kernels instantiated for complex128 -----------------------
 // (16-byte elements: E = 10 / 8 keeps the line in <= 64 data registers)
+typedef MixPlan3<2000, 10, 20> MP2000;      // 10 x 20 x 10: two exchanges per transform instead of the three of 10 x 10 x 10 x 2
 typedef LinePlan<256, 8, 8, 8, 4> LP256E8;
 typedef LinePlan<200, 10, 10, 10, 2> LP200E10;
 
@@ -142,26 +143,47 @@ SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant) {
             if (variant == 1) P3D_COLS64(LP1000, 4, 1, "spec64<1000,E10,10x10x10,C4,1cta>");
             else if (variant == 2) P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta>");
             else if (variant == 3) P3D_COLS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,C2,2cta>");
-            else { P3D_COLS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,C2,2cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 2, 2, true, double>; }
+            else if (variant == 4) { P3D_COLS64(LP1000, 1, 5, "spec64<1000,E10,10x10x10,C1,5cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 1, 5, true, double>; }
+            else if (variant == 5) { P3D_COLS64(LP1000, 1, 4, "spec64<1000,E10,10x10x10,C1,4cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 1, 4, true, double>; }
+            else if (variant == 6) { P3D_COLS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,C2,2cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 2, 2, true, double>; }
+            else if (variant == 7) { P3D_COLS64(LP1000, 4, 1, "spec64<1000,E10,10x10x10,C4,1cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 4, 1, true, double>; }
+            else if (variant == 8) { P3D_COLS64(LP1000, 4, 2, "spec64<1000,E10,10x10x10,C4,2cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000, 4, 2, true, double, true>; }
+            else if (variant == 9) { P3D_COLS64(LP1000, 2, 4, "spec64<1000,E10,10x10x10,C2,4cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000, 2, 4, true, double, true>; }
+            else if (variant == 10) { P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000, 2, 3, true, double, true>; }
+            else { P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 2, 3, true, double>; }
             break;
         case 2000:
             if (variant == 1) P3D_COLS64(LP2000, 1, 3, "spec64<2000,E10,10x10x10x2,C1,3cta>");
-            else              P3D_COLS64(LP2000, 2, 1, "spec64<2000,E10,10x10x10x2,C2,1cta>");
+            else if (variant == 2) P3D_COLS64(LP2000, 2, 1, "spec64<2000,E10,10x10x10x2,C2,1cta>");
+            else if (variant == 3) { P3D_COLS64(MP2000, 1, 3, "mix64<2000,10x20x10,C1,3cta,cp.async>"); k.cols_iter = launch_cols<MP2000, 1, 3, true, double>; }
+            else if (variant == 4) { P3D_COLS64(MP2000, 2, 1, "mix64<2000,10x20x10,C2,1cta,cp.async>"); k.cols_iter = launch_cols<MP2000, 2, 1, true, double>; }
+            else if (variant == 5) { P3D_COLS64(MP2000, 1, 2, "mix64<2000,10x20x10,C1,2cta,cp.async>"); k.cols_iter = launch_cols<MP2000, 1, 2, true, double>; }
+            else { P3D_COLS64(MP2000, 2, 2, "mix64<2000,10x20x10,C2,2cta,cp.async,1buf>"); k.cols_iter = launch_cols<MP2000, 2, 2, true, double, true>; }
             break;
         case 256:  P3D_COLS64(LP256E8, 8, 3, "spec64<256,E8,8x8x4,C8>"); break;
         case 200:  P3D_COLS64(LP200E10, 8, 4, "spec64<200,E10,10x10x2,C8>"); break;
+        case 847:  P3D_COLS64(MP847, 2, 3, "mix64<847,11x7x11,C2,3cta>"); break;
         default: break;
     }
     switch (n_xline) {
         case 1000:
             if (variant == 1) P3D_ROWS64(LP1000, 2, 2, "spec64<1000,E10,10x10x10,RB2,2cta>");
-            else              P3D_ROWS64(LP1000, 1, 5, "spec64<1000,E10,10x10x10,RB1,5cta>");
+            else if (variant == 4 || variant == 6) P3D_ROWS64(LP1000, 1, 5, "spec64<1000,E10,10x10x10,RB1,5cta>");
+            else if (variant == 5 || variant == 7) P3D_ROWS64(LP1000, 1, 6, "spec64<1000,E10,10x10x10,RB1,6cta>");
+            else if (variant == 8) P3D_ROWS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,RB2,3cta>");
+            else if (variant == 9) P3D_ROWS64(LP1000, 3, 2, "spec64<1000,E10,10x10x10,RB3,2cta>");
+            else if (variant == 10) P3D_ROWS64(LP1000, 4, 1, "spec64<1000,E10,10x10x10,RB4,1cta>");
+            else              P3D_ROWS64(LP1000, 1, 4, "spec64<1000,E10,10x10x10,RB1,4cta>");
             break;
         case 2000:
-            P3D_ROWS64(LP2000, 1, 2, "spec64<2000,E10,10x10x10x2,RB1,2cta>");
+            if (variant == 1 || variant == 2) P3D_ROWS64(LP2000, 1, 2, "spec64<2000,E10,10x10x10x2,RB1,2cta>");
+            else if (variant == 3) P3D_ROWS64(MP2000, 1, 3, "mix64<2000,10x20x10,RB1,3cta>");
+            else if (variant == 4) P3D_ROWS64(MP2000, 1, 4, "mix64<2000,10x20x10,RB1,4cta>");
+            else P3D_ROWS64(MP2000, 1, 2, "mix64<2000,10x20x10,RB1,2cta>");
             break;
         case 256:  P3D_ROWS64(LP256E8, 4, 5, "spec64<256,E8,8x8x4,RB4>"); break;
         case 200:  P3D_ROWS64(LP200E10, 4, 6, "spec64<200,E10,10x10x2,RB4>"); break;
+        case 847:  P3D_ROWS64(MP847, 1, 5, "mix64<847,11x7x11,RB1,5cta>"); break;
         default: break;
     }
     return k;

@@ -25,6 +25,22 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 __device__ __forceinline__ double warp_sum_f(double v) { return warp_sum(v); }
 
+// |x| for the convergence sum.  double: an fp32 reciprocal-square-root seed and one Newton step in double (1e-14
+// relative) instead of the library square root (a dozen FP64 instructions and a slow-path call per element); values
+// outside the float range take the library path.
+__device__ __forceinline__ float norm_sqrt(float v) { return sqrtf(v); }
+__device__ __forceinline__ double norm_sqrt(double v) {
+    if (!(v > 1e-30 && v < 1e30)) return sqrt(v);
+    const double r = (double)rsqrtf((float)v);
+    const double y = v * r;
+    return fma(fma(-y, y, v), 0.5 * r, y);
+}
+
+// plans whose transforms may run on a single exchange buffer (ColAcc1): every LinePlan; a MixPlan3 only when its middle
+// pass is one round (operands in registers before the first write)
+template <typename LP> struct single_buffer_ok { static constexpr bool value = true; };
+template <int N, int Ra, int Rb> struct single_buffer_ok<MixPlan3<N, Ra, Rb>> { static constexpr bool value = MixPlan3<N, Ra, Rb>::SINGLE_BUFFER_OK; };
+
 // ---- column kernel ---------------------------------------------------------------------------------
 // BULK: the tile is loaded with cp.async.cg (global -> shared memory in 16-byte pieces, no register and no L1 staging)
 // into exchange buffer 1, which is free until the second exchange, in the [row][c] layout of the accessor, and read
@@ -38,6 +54,7 @@ __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A, const int op) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
+    static_assert(!SB || single_buffer_ok<LP>::value, "this plan needs two exchange buffers");
     const int s = band_slice(A);
     const int tid = threadIdx.x;
     const int c = tid % C, j = tid / C;
@@ -191,8 +208,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     const long long midx = (A.first_slice + s) / G.slices_per_mask;
     const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
     if (stopped != 0 || slice_frozen(A, s)) return;
-    if (sizeof(F) == 4 && A.astart && blockIdx.x == 0 && tid == 0)
-        A.astart[(long long)s * (A.niter + 1) + A.k + 1] = A.acnt[s];          // end of this iteration's support record
+    if (sizeof(F) == 4 && A.astart && blockIdx.x == 0 && tid == 0) close_support_record(A, s);
 
     LP::template fft<+1, 0, F>(v, acc, j, tw);
 
@@ -207,7 +223,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
             const F m = ((mbits >> e) & 1u) ? F(1) : F(0);
             const F coef = (F(1) - A.alpha * m) * A.inv_n;
             Cx<F> x = cmake<F>(fma(coef, v[e].x, A.alpha * d[e].x), fma(coef, v[e].y, A.alpha * d[e].y));
-            part += sqrt(x.x * x.x + x.y * x.y);
+            part += norm_sqrt(x.x * x.x + x.y * x.y);
             if (A.write_out) Op[e * T] = cmake<FD>((FD)x.x, (FD)x.y);
             if (A.adaptive) {
                 const F keep = F(1) - A.alpha * m, om = F(1) - A.alpha;

@@ -363,11 +363,11 @@ def test_f64_mode_register_kernels_match_generic(shape, op, model, alpha, versio
     x = np.stack([x, 0.5 * x[::-1, ::-1] * mask]).astype(np.complex64)
     params = dict(niter=9, thresh_op=op, thresh_model=model, eps=0.0, alpha=alpha, p_max=0.99, p_min=1e-3)
     plan = p3d.PocsPlan(*shape, precision=64)
-    assert "spec64<" in plan.describe()
+    assert "spec64<" in plan.describe() or "mix64<" in plan.describe()
     y, info = plan.run(x, mask, version=version, want_costs=True, **params)
     gen = p3d.PocsPlan(*shape, precision=64)
     gen.set_option("force_generic", 1)
-    assert "spec64<" not in gen.describe()
+    assert "spec64<" not in gen.describe() and "mix64<" not in gen.describe()
     yg, infog = gen.run(x, mask, version=version, want_costs=True, **params)
     assert rel_l2(y, yg) <= 2e-7
     np.testing.assert_allclose(info["costs"], infog["costs"], rtol=1e-3, atol=1e-22)   # tiny costs = cancelling sums

@@ -42,6 +42,8 @@ def main():
         plan.set_option("lanes", int(a[9]))
     if len(a) > 10:
         plan.set_option("spec_variant64", int(a[10]))
+    if os.environ.get("P3D_GUARD"):
+        plan.set_option("guard_factor", int(float(os.environ["P3D_GUARD"])))
     print(plan.describe())
     dx = _lib.DeviceBuffer(x.nbytes); dx.upload(x)
     dm = _lib.DeviceBuffer(mask.nbytes); dm.upload(mask)
@@ -63,7 +65,7 @@ def main():
     for k, v in prof.items():
         if v["launches"]:
             per = v["ms"] / v["launches"]
-            bytes_alg = {"cols_iter": 32, "rows_iter": 41, "rows_init": 16, "cols_stats": 8}.get(k, 0) * ne * (band if band else ns)
+            bytes_alg = {"cols_iter": 16, "rows_iter": 24.125, "rows_init": 16, "cols_stats": 8, "cols_iter64": 32, "rows_iter64": 40.125}.get(k, 0) * ne * (band if band else ns)
             print(f"  {k:10s} launches={v['launches']:5d} total={v['ms']:9.3f} ms  avg={per*1e3:9.1f} us  alg GB/s={bytes_alg / (per * 1e-3) / 1e9 if per else 0:8.1f}")
     out = np.empty_like(x[:1]); do.download(out)
     print("checksum", float(np.abs(out).sum()))
