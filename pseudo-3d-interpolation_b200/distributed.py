@@ -9,6 +9,8 @@ CPU with the gloo backend.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .pocs import band_bounds
@@ -100,7 +102,7 @@ def pocs_cube_distributed(cube, fold_or_mask, process_fn=None, gather_to=0, grou
     t = torch.from_numpy(pad)
     backend = dist.get_backend(group)
     if backend == "nccl":
-        t = t.cuda()
+        t = t.to(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     parts = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(parts, t, group=group)
     if rank != gather_to:
@@ -184,10 +186,17 @@ def _gpu_steps(device, n_il, n_xl, twt, compute_real, precision, metadata):
     dt, t0 = float(twt[1] - twt[0]), float(twt[0])
     nf = nt // 2 + 1 if compute_real else nt
     dev = torch.device("cuda", device)
+    torch.cuda.set_device(dev)                 # collectives and `.cuda()` copies of this process target the rank's own GPU
+
+    def drain():
+        # the library runs on its own non-blocking streams: everything torch enqueued (all-to-all, repacking copies,
+        # uploads) must have finished before a library call reads it, and vice versa the library calls return drained
+        torch.cuda.current_stream(dev).synchronize()
 
     def fft_fn(x_local):                       # (nt, ntr_loc) float32 host -> (nf, ntr_loc) complex64 device
         xd = torch.from_numpy(x_local).to(dev)
         F = torch.empty((nf, x_local.shape[1]), dtype=torch.complex64, device=dev)
+        drain()
         _lib.check(lib.p3d_time_fft(device, C.c_void_p(xd.data_ptr()), _lib.MEM_DEVICE, C.c_void_p(F.data_ptr()), _lib.MEM_DEVICE,
                                     nt, nt, x_local.shape[1], dt, t0, 1 if compute_real else 0, None))
         return F
@@ -196,12 +205,14 @@ def _gpu_steps(device, n_il, n_xl, twt, compute_real, precision, metadata):
         out = torch.empty_like(band)
         md = torch.from_numpy(mask).to(dev)
         nit = np.zeros(band.shape[0], np.int32)
+        drain()
         if band.shape[0]:
             get_plan(n_il, n_xl, device, precision).run_device(band.data_ptr(), md.data_ptr(), out.data_ptr(), band.shape[0], params, nit=nit)
         return out, nit
 
     def ifft_fn(F_local):                      # (nf, ntr_loc) complex64 device -> (nt, ntr_loc) float32 host
         x = torch.empty((nt, F_local.shape[1]), dtype=torch.float32, device=dev)
+        drain()
         _lib.check(lib.p3d_time_ifft(device, C.c_void_p(F_local.data_ptr()), _lib.MEM_DEVICE, C.c_void_p(x.data_ptr()), _lib.MEM_DEVICE,
                                      nt, nt, F_local.shape[1], dt, t0, 1 if compute_real else 0, 0))
         return x.cpu().numpy()
@@ -266,7 +277,7 @@ def interpolate_time_cube_distributed(x, twt, fold, compute_real=True, steps=Non
     pad[:, : i1 - i0] = local
     t = torch.from_numpy(pad)
     if dist.get_backend(group) == "nccl":
-        t = t.cuda()
+        t = t.to(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     parts = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(parts, t, group=group)
     if rank != gather_to:
