@@ -45,8 +45,9 @@ struct Lane {
     int* list = nullptr; int* h_list = nullptr;
     double2* cand = nullptr; int cand_stride = 0;
     unsigned* arena = nullptr; int* acnt = nullptr; int* astart = nullptr; int* h_astart = nullptr; double2* yval = nullptr;
+    int* wflag = nullptr; int* kfail = nullptr; int* kend = nullptr; int* h_wflag = nullptr; int* h_kfail = nullptr; int* h_kend = nullptr;
     int arena_cap = 0;
-    int64_t n_escalated = 0, n_esc_iters = 0;
+    int64_t n_escalated = 0, n_esc_iters = 0, n_verify_failed = 0;
     unsigned long long* dd_keys = nullptr; unsigned int* dd_vals = nullptr; int64_t dd_ne = 0;   // exact data-driven schedule scratch
     // CUB scratch of the data-driven schedule (per lane: lanes sort concurrently on their own streams)
     void* cub_temp = nullptr; size_t cub_temp_bytes = 0;
@@ -72,6 +73,9 @@ struct p3d_plan {
     double guard_factor = 1024.0;    // guard half-width in units of eps32 * rms|X| (escalating mode)
     int seg_iters = 4;               // escalating mode: iterations between two compactions of the active-slice list
     int arena_cap = 16384;           // escalating mode: support-record entries per slice (all pilot iterations together)
+    int watch_mode = -1;             // escalating mode: guard-band hits are verified by the float64 replay instead of freezing the slice
+                                     // (-1 = where it pays: slices of 400 k points and more; small slices freeze on the first hit -
+                                     // their replay launches cost more than the complex128 iterations they would save)
     int support_cap = 0;             // escalating mode: largest support replayed per iteration (0 = 4 sqrt(n1 n2): where one more
                                      // replayed iteration, ~|S|^2 gathers, costs what the complex128 iteration it replaces does)
     Cx<double>* mhat = nullptr; int64_t mhat_masks = 0;          // fft2 of the mask planes in complex128 (exact restart)
@@ -156,6 +160,9 @@ void free_lane(Lane& L) {
     if (L.astart) cudaFree(L.astart);
     if (L.yval) cudaFree(L.yval);
     if (L.h_astart) cudaFreeHost(L.h_astart);
+    for (int* p : {L.wflag, L.kfail, L.kend}) if (p) cudaFree(p);
+    for (int* p : {L.h_wflag, L.h_kfail, L.h_kend}) if (p) cudaFreeHost(p);
+    L.wflag = L.kfail = L.kend = L.h_wflag = L.h_kfail = L.h_kend = nullptr;
     L.arena = nullptr; L.acnt = nullptr; L.astart = nullptr; L.yval = nullptr; L.h_astart = nullptr; L.arena_cap = 0;
     if (L.h_tau64) cudaFreeHost(L.h_tau64);
     if (L.h_esc) cudaFreeHost(L.h_esc);
@@ -212,6 +219,12 @@ void ensure_lane(p3d_plan* P, Lane& L, int64_t cap, int niter, bool need_d, bool
         P3D_CUDA(cudaMalloc(&L.acnt, sizeof(int) * cap));
         P3D_CUDA(cudaMalloc(&L.astart, sizeof(int) * cap * (niter + 1)));
         P3D_CUDA(cudaMallocHost(&L.h_astart, sizeof(int) * cap * (niter + 1)));
+        P3D_CUDA(cudaMalloc(&L.wflag, sizeof(int) * cap));
+        P3D_CUDA(cudaMalloc(&L.kfail, sizeof(int) * cap));
+        P3D_CUDA(cudaMalloc(&L.kend, sizeof(int) * cap));
+        P3D_CUDA(cudaMallocHost(&L.h_wflag, sizeof(int) * cap));
+        P3D_CUDA(cudaMallocHost(&L.h_kfail, sizeof(int) * cap));
+        P3D_CUDA(cudaMallocHost(&L.h_kend, sizeof(int) * cap));
         L.has_esc = true; L.cand_stride = std::max(1, cand_stride);
     }
     L.cap = cap; L.niter_cap = niter;
@@ -757,11 +770,11 @@ __global__ void k_mask_to_c64(const uint8_t* __restrict__ m, Cx<float>* __restri
 }
 
 // ascending sort of every (slice, iteration) segment of the support record: the replay sums in a fixed order
-__global__ void k_sort_segments(const int* __restrict__ list, const int* __restrict__ esc, unsigned* arena, const int* __restrict__ astart,
+__global__ void k_sort_segments(const int* __restrict__ list, const int* __restrict__ kend, unsigned* arena, const int* __restrict__ astart,
                                 int acap, int niter) {
     extern __shared__ unsigned seg_sh[];
     const int s = list[blockIdx.y], i = blockIdx.x;
-    if (i >= esc[s] - 1) return;
+    if (i >= kend[s]) return;
     const int a0 = astart[(long long)s * (niter + 1) + i], n = astart[(long long)s * (niter + 1) + i + 1] - a0;
     if (n <= 1) return;
     int m = 1; while (m < n) m <<= 1;
@@ -786,14 +799,14 @@ __global__ void k_sort_segments(const int* __restrict__ list, const int* __restr
 // one iteration of the sparse-domain float64 recursion (see the header of this section)
 template <int OP>
 __global__ void __launch_bounds__(128)
-k_replay(const int i, const int* __restrict__ list, const int* __restrict__ esc, const unsigned* __restrict__ arena,
+k_replay(const int i, const int* __restrict__ list, const int* __restrict__ kend, int* __restrict__ kfail, const unsigned* __restrict__ arena,
          const int* __restrict__ astart, double2* __restrict__ yval, const int acap, const int niter,
          const Cx<double>* __restrict__ X0, const Cx<double>* __restrict__ mhat, const Cx<double>* __restrict__ tau,
          const long long first_slice, const int spm, const int n1, const int n2, const double alpha, const double inv_n) {
     __shared__ unsigned sp[128];
     __shared__ double2 sy[128];
     const int s = list[blockIdx.y];
-    if (i >= esc[s] - 1) return;
+    if (i >= kend[s]) return;
     const int* as = astart + (long long)s * (niter + 1);
     const int a0 = as[i], n = as[i + 1] - a0;
     if ((int)blockIdx.x * 128 >= n) return;
@@ -802,7 +815,9 @@ k_replay(const int i, const int* __restrict__ list, const int* __restrict__ esc,
     const bool valid = t < n;
     const unsigned* ar = arena + (long long)s * acap;
     double2* yv = yval + (long long)s * acap;
-    const unsigned pj = valid ? ar[a0 + t] : 0u;
+    const unsigned ent = valid ? ar[a0 + t] : 0u;
+    const bool watched = (ent >> 31) != 0u;           // killed by the pilot inside the guard band: verify, contributes nothing
+    const unsigned pj = ent & 0x7fffffffu;
     const int jr = (int)(pj >> 16), jc = (int)(pj & 0xffffu);
     const long long ne = (long long)n1 * n2;
     const Cx<double> x0 = valid ? X0[(long long)s * ne + (long long)jr * n2 + jc] : cmake<double>(0.0, 0.0);
@@ -811,7 +826,7 @@ k_replay(const int i, const int* __restrict__ list, const int* __restrict__ esc,
     for (int q0 = 0; q0 < np; q0 += 128) {
         const int nq = min(128, np - q0);
         __syncthreads();
-        if ((int)threadIdx.x < nq) { sp[threadIdx.x] = ar[p0 + q0 + threadIdx.x]; sy[threadIdx.x] = yv[p0 + q0 + threadIdx.x]; }
+        if ((int)threadIdx.x < nq) { sp[threadIdx.x] = ar[p0 + q0 + threadIdx.x] & 0x7fffffffu; sy[threadIdx.x] = yv[p0 + q0 + threadIdx.x]; }
         __syncthreads();
         if (valid) {
             // eight gathers in flight per thread (the mhat plane lives in L2: latency, not bandwidth, bounds this loop)
@@ -850,7 +865,12 @@ k_replay(const int i, const int* __restrict__ list, const int* __restrict__ esc,
     if (i > 0) X = cmake<double>(alpha * x0.x + selfx - alpha * inv_n * accx, alpha * x0.y + selfy - alpha * inv_n * accy);
     const Cx<double> tk = tau[(long long)s * niter + i];
     const double a = tk.x, b = tk.y;
-    const Cx<double> y = apply_threshold<OP, double>(X, a, b, a * a - b * b, 2.0 * a * b);
+    Cx<double> y = apply_threshold<OP, double>(X, a, b, a * a - b * b, 2.0 * a * b);
+    // the pilot's decision against the exact one: a kept coefficient must survive the float64 threshold, a watched one
+    // must not; the first iteration with a mismatch is where complex128 has to take over
+    const bool survives = (y.x != 0.0) || (y.y != 0.0);
+    if (survives == watched) atomicMin(&kfail[s], i);
+    if (watched) y = cmake<double>(0.0, 0.0);
     yv[a0 + t] = make_double2(y.x, y.y);
 }
 
@@ -860,15 +880,24 @@ __global__ void k_zero_slices(const int* __restrict__ list, Cx<double>* W, long 
     double2* w = reinterpret_cast<double2*>(W + (long long)s * ne);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) w[i] = make_double2(0.0, 0.0);
 }
+// sums |x_k| that complex128 will (re)compute: from the restart iteration on (a slice reopened by the verification has
+// fp32 sums there)
+__global__ void k_zero_sums(const int* __restrict__ list, const int* __restrict__ esc, double* S, int niter, int n) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int s = list[r];
+    const int ke = esc[s] - 1;
+    for (int q = ke > 1 ? ke : 1; q <= niter; ++q) S[(long long)s * (niter + 1) + q] = 0.0;
+}
 __global__ void k_scatter_restart(const int* __restrict__ list, const int* __restrict__ esc, const unsigned* __restrict__ arena,
                                   const int* __restrict__ astart, const double2* __restrict__ yval, int acap, int niter,
                                   Cx<double>* W, int n2, long long ne, double* S) {
     const int s = list[blockIdx.y];
     const int ke = esc[s] - 1;              // >= 1 for every slice of this list
     const int a0 = astart[(long long)s * (niter + 1) + ke - 1], n = astart[(long long)s * (niter + 1) + ke] - a0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) S[(long long)s * (niter + 1) + ke] = 0.0;      // sum |x_{k_e - 1}| is recomputed in double
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const unsigned pj = arena[(long long)s * acap + a0 + t];
+        if (pj >> 31) continue;                     // a watched kill: not part of the spectrum
         const double2 y = yval[(long long)s * acap + a0 + t];
         W[(long long)s * ne + (long long)(pj >> 16) * n2 + (pj & 0xffffu)] = cmake<double>(y.x, y.y);
     }
@@ -898,6 +927,8 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     P3D_CUDA(cudaMemsetAsync(L.esc, 0, sizeof(int) * count, st));
     P3D_CUDA(cudaMemsetAsync(L.acnt, 0, sizeof(int) * count, st));
     P3D_CUDA(cudaMemsetAsync(L.astart, 0, sizeof(int) * count * (niter + 1), st));
+    P3D_CUDA(cudaMemsetAsync(L.wflag, 0, sizeof(int) * count, st));
+    P3D_CUDA(cudaMemsetAsync(L.kfail, 0x7f, sizeof(int) * count, st));
     for (int64_t i = 0; i < count; ++i) {
         memset(&L.h_stats[i], 0, sizeof(SliceStats));
         L.h_stats[i].minabs_bits = 0x7f800000u;
@@ -1108,6 +1139,11 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             if (guard_on) {
                 B.arena = L.arena; B.acnt = L.acnt; B.astart = L.astart; B.arena_cap = acap;
                 B.scap = P->support_cap > 0 ? P->support_cap : (int)(4.0 * std::sqrt((double)ne));
+                // watch list (kernels that record the guard band; bit 31 of an entry must be free): a hit is verified by
+                // the replay instead of freezing the slice
+                const bool want_watch = P->watch_mode < 0 ? (ne >= 400000) : (P->watch_mode != 0);
+                B.watch = (want_watch && P->spec.cols_iter && !P->force_generic && P->n1 < 32768 && !adaptive) ? 1 : 0;
+                B.wflag = L.wflag;
             }
             B.k = k; B.last = (k == niter - 1) ? 1 : 0;
             B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
@@ -1129,23 +1165,97 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
         }
     }
 
-    // ---- phase 2: exact restart + complex128 iterations of the frozen slices ---------------------------------------
+    // ---- phase 2: replay + verification, exact restart, complex128 iterations of the frozen slices -----------------------
     if (guard_on) {
         P3D_CUDA(cudaMemcpyAsync(L.h_esc, L.esc, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
         P3D_CUDA(cudaMemcpyAsync(L.h_stop, L.stop, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+        P3D_CUDA(cudaMemcpyAsync(L.h_wflag, L.wflag, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
         P3D_CUDA(cudaMemcpyAsync(L.h_astart, L.astart, sizeof(int) * count * (niter + 1), cudaMemcpyDeviceToHost, st));
         P3D_CUDA(cudaStreamSynchronize(st));
-        std::vector<std::pair<int, int>> e64;       // (k_e = first complex128 iteration, slice)
-        for (int64_t i = 0; i < count; ++i)
-            if (L.h_esc[i] > 0 && L.h_stop[i] == 0) e64.push_back(std::make_pair(L.h_esc[i] - 1, (int)i));
+        // replay: frozen slices up to their switch iteration; slices that finished (or stopped) in fp32 but recorded
+        // watched decisions are replayed over everything they ran, for the verification alone
+        std::vector<int> rl;
+        int kmax = 0, seg_max = 0;
+        for (int64_t i = 0; i < count; ++i) {
+            int kend = 0;
+            if (L.h_stop[i] < 0) kend = 0;
+            else if (L.h_esc[i] > 0 && L.h_stop[i] == 0) kend = L.h_esc[i] - 1;
+            else if (L.h_wflag[i]) kend = L.h_stop[i] > 0 ? L.h_stop[i] : niter;
+            L.h_kend[i] = kend;
+            if (kend > 0) { rl.push_back((int)i); kmax = std::max(kmax, kend); }
+        }
+        if (!rl.empty()) {
+            prof_begin(P, L.events, st, 11);
+            std::vector<int> smax((size_t)kmax, 0);
+            for (int i : rl) {
+                const int* as = L.h_astart + (int64_t)i * (niter + 1);
+                for (int q = 0; q < L.h_kend[i]; ++q) { smax[q] = std::max(smax[q], as[q + 1] - as[q]); seg_max = std::max(seg_max, as[q + 1] - as[q]); }
+            }
+            upload_list(rl);
+            P3D_CUDA(cudaMemcpyAsync(L.kend, L.h_kend, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+            const int nrl = (int)rl.size();
+            int pow2 = 1; while (pow2 < seg_max) pow2 <<= 1;
+            static bool sort_cfg = false;
+            if (!sort_cfg) { cudaFuncSetAttribute(k_sort_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4); sort_cfg = true; }
+            for (int64_t o = 0; o < nrl; o += band_max) {
+                const int nb = (int)std::min<int64_t>(band_max, nrl - o);
+                k_sort_segments<<<dim3((unsigned)kmax, (unsigned)nb), 256, sizeof(unsigned) * pow2, st>>>(L.list + o, L.kend, L.arena, L.astart, acap, niter);
+            }
+            for (int i = 0; i < kmax; ++i) {
+                if (smax[i] == 0) continue;
+                const unsigned gx = (unsigned)((smax[i] + 127) / 128);
+                for (int64_t o = 0; o < nrl; o += band_max) {
+                    const int nb = (int)std::min<int64_t>(band_max, nrl - o);
+                    const dim3 grid(gx, (unsigned)nb);
+#define P3D_REPLAY(OPV) k_replay<OPV><<<grid, 128, 0, st>>>(i, L.list + o, L.kend, L.kfail, L.arena, L.astart, L.yval, acap, niter, L.W64, P->mhat, L.tau64, \
+                                                            (long long)first, (int)std::min<int64_t>(R.spm, 0x7fffffff), P->n1, P->n2, pr.alpha, A64.inv_n)
+                    if (pr.thresh_op == P3D_OP_HARD) P3D_REPLAY(P3D_OP_HARD);
+                    else if (pr.thresh_op == P3D_OP_SOFT) P3D_REPLAY(P3D_OP_SOFT);
+                    else P3D_REPLAY(P3D_OP_GARROTE);
+#undef P3D_REPLAY
+                }
+            }
+            prof_end(P, L.events, st);
+            P3D_CUDA(cudaGetLastError());
+            P3D_CUDA(cudaMemcpyAsync(L.h_kfail, L.kfail, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+            P3D_CUDA(cudaStreamSynchronize(st));
+        }
+        // first complex128 iteration of every slice: its freeze point, or earlier where the verification found the pilot's
+        // decision to differ from the exact one (everything the pilot did from there on is discarded)
+        std::vector<std::pair<int, int>> e64;       // (k_e, slice)
+        bool esc_changed = false;
+        for (int64_t i = 0; i < count; ++i) {
+            if (L.h_stop[i] < 0) continue;
+            int ke = (L.h_esc[i] > 0 && L.h_stop[i] == 0) ? L.h_esc[i] - 1 : -1;
+            if (L.h_kend[i] > 0 && L.h_kfail[i] < L.h_kend[i]) {
+                ke = L.h_kfail[i];
+                L.h_esc[i] = ke + 1; L.h_stop[i] = 0; esc_changed = true;
+                L.n_verify_failed += 1;
+            }
+            if (ke >= 0) e64.push_back(std::make_pair(ke, (int)i));
+        }
+        if (esc_changed) {
+            // (a slice the pilot had stopped early on its cost is reopened: the complex128 kernels decide again)
+            P3D_CUDA(cudaMemcpyAsync(L.esc, L.h_esc, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+            P3D_CUDA(cudaMemcpyAsync(L.stop, L.h_stop, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+        }
         std::sort(e64.begin(), e64.end());
         if (!e64.empty()) {
             const int n64 = (int)e64.size();
             std::vector<int> order((size_t)n64);
-            int n0 = 0;                              // slices frozen in the very first iteration: restart state = d
-            for (int r = 0; r < n64; ++r) { order[r] = e64[r].second; if (e64[r].first == 0) ++n0; }
+            int n0 = 0;                              // slices whose first iteration already belongs to complex128: restart state = d
+            int smax_restart = 1;
+            for (int r = 0; r < n64; ++r) {
+                order[r] = e64[r].second;
+                if (e64[r].first == 0) ++n0;
+                else {
+                    const int* as = L.h_astart + (int64_t)e64[r].second * (niter + 1);
+                    smax_restart = std::max(smax_restart, as[e64[r].first] - as[e64[r].first - 1]);
+                }
+            }
             upload_list(order);
-            const int n1r = n64 - n0;                // slices with a replay
+            k_zero_sums<<<(unsigned)((n64 + 127) / 128), 128, 0, st>>>(L.list, L.esc, L.S, niter, n64);
+            const int n1r = n64 - n0;                // slices restarted from a replayed spectrum
             const int* list1 = L.list + n0;
             if (n0 > 0) {
                 BandArgs<double> B64 = A64;
@@ -1154,40 +1264,11 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             }
             if (n1r > 0) {
                 prof_begin(P, L.events, st, 11);
-                const int kmax = e64.back().first;                       // replay iterations 0 .. kmax - 1
-                // largest support per replay iteration (over the slices that need it) sizes the launches
-                std::vector<int> smax((size_t)kmax, 0);
-                int seg_max = 0;
-                for (int r = n0; r < n64; ++r) {
-                    const int* as = L.h_astart + (int64_t)e64[r].second * (niter + 1);
-                    for (int i = 0; i < e64[r].first; ++i) { smax[i] = std::max(smax[i], as[i + 1] - as[i]); seg_max = std::max(seg_max, as[i + 1] - as[i]); }
-                }
-                int pow2 = 1; while (pow2 < seg_max) pow2 <<= 1;
-                static bool sort_cfg = false;
-                if (!sort_cfg) { cudaFuncSetAttribute(k_sort_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4); sort_cfg = true; }
-                for (int64_t o = 0; o < n1r; o += band_max) {
-                    const int nb = (int)std::min<int64_t>(band_max, n1r - o);
-                    k_sort_segments<<<dim3((unsigned)kmax, (unsigned)nb), 256, sizeof(unsigned) * pow2, st>>>(list1 + o, L.esc, L.arena, L.astart, acap, niter);
-                }
-                for (int i = 0; i < kmax; ++i) {
-                    if (smax[i] == 0) continue;
-                    const unsigned gx = (unsigned)((smax[i] + 127) / 128);
-                    for (int64_t o = 0; o < n1r; o += band_max) {
-                        const int nb = (int)std::min<int64_t>(band_max, n1r - o);
-                        const dim3 grid(gx, (unsigned)nb);
-#define P3D_REPLAY(OPV) k_replay<OPV><<<grid, 128, 0, st>>>(i, list1 + o, L.esc, L.arena, L.astart, L.yval, acap, niter, L.W64, P->mhat, L.tau64, \
-                                                            (long long)first, (int)std::min<int64_t>(R.spm, 0x7fffffff), P->n1, P->n2, pr.alpha, A64.inv_n)
-                        if (pr.thresh_op == P3D_OP_HARD) P3D_REPLAY(P3D_OP_HARD);
-                        else if (pr.thresh_op == P3D_OP_SOFT) P3D_REPLAY(P3D_OP_SOFT);
-                        else P3D_REPLAY(P3D_OP_GARROTE);
-#undef P3D_REPLAY
-                    }
-                }
                 for (int64_t o = 0; o < n1r; o += band_max) {
                     const int nb = (int)std::min<int64_t>(band_max, n1r - o);
                     k_zero_slices<<<dim3((unsigned)std::min<long long>((ne + 255) / 256, 592), (unsigned)nb), 256, 0, st>>>(list1 + o, L.W64, ne);
-                    k_scatter_restart<<<dim3((unsigned)std::max(1, (seg_max + 255) / 256), (unsigned)nb), 256, 0, st>>>(list1 + o, L.esc, L.arena, L.astart, L.yval, acap, niter,
-                                                                                                                     L.W64, P->n2, ne, L.S);
+                    k_scatter_restart<<<dim3((unsigned)((smax_restart + 255) / 256), (unsigned)nb), 256, 0, st>>>(list1 + o, L.esc, L.arena, L.astart, L.yval, acap, niter,
+                                                                                                            L.W64, P->n2, ne, L.S);
                 }
                 prof_end(P, L.events, st);
                 P3D_CUDA(cudaGetLastError());
@@ -1304,7 +1385,7 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     const int lanes = pr->thresh_percentile ? 1 : (P->n_lanes > 0 ? P->n_lanes : ((host_in || host_out) ? 4 : 1));
     if ((int)P->lanes.size() < lanes) P->lanes.resize(lanes);
     const int nbuf = 1 + (host_in ? 1 : 0) + (host_out ? 1 : 0) + (escalate ? 2 : 0);
-    for (auto& L : P->lanes) { L.pending = false; L.n_escalated = 0; L.n_esc_iters = 0; }
+    for (auto& L : P->lanes) { L.pending = false; L.n_escalated = 0; L.n_esc_iters = 0; L.n_verify_failed = 0; }
     int cand_stride = 0;
     if (escalate) {
         if (!P->f64) { P->f64 = f64_create(P->device, P->n1, P->n2, &P->ax1, &P->ax2, P->smem_optin); f64_install_spec(P->f64, P->spec_variant64); }
@@ -1606,8 +1687,9 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     }
     else if (!strcmp(key, "guard_factor")) P->guard_factor = (double)value;
     else if (!strcmp(key, "seg_iters")) P->seg_iters = (int)std::max<int64_t>(1, value);
+    else if (!strcmp(key, "watch_mode")) P->watch_mode = (int)value;
     else if (!strcmp(key, "support_cap")) P->support_cap = (int)std::max<int64_t>(0, value);
-    else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(128, value));
+    else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(32768, std::max<int64_t>(128, value));
     else if (!strcmp(key, "spec_variant")) {
         try { DeviceGuard g(P->device); install_spec(P, (int)value); } catch (const P3dFail& f) { return f.code; }
     }

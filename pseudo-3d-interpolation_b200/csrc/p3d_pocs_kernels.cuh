@@ -105,6 +105,9 @@ template <typename T> struct BandArgs {
     int* astart;                 // [band][niter + 1] first entry of iteration k (astart[.][0] = 0)
     int arena_cap;
     int scap;                    // freeze the slice after an iteration that kept more than scap coefficients (replay cost ~ |S|^2)
+    int watch;                   // 1: a guard-band hit does not freeze the slice; killed coefficients inside the band are recorded
+                                 // too (bit 31 set) and the float64 replay verifies every decision inside the band exactly
+    int* wflag;                  // [band] set when a slice has recorded such a "watched kill"
     int restart;                 // complex128 kernels: this launch rebuilds x_{k_e - 1} (iteration index = esc[s] - 2 per slice)
     int store_x0_inplace;        // complex128 statistics kernel: leave X0 in W
 };
@@ -141,10 +144,14 @@ template <typename T> __device__ __forceinline__ bool slice_frozen(const BandArg
 
 // Append the packed indices of the coefficients this CTA kept to the slice's support record.  kept: bit e <-> idx[e].
 // sh: >= 34 ints of shared memory.  Every thread of the CTA must call this (barriers inside).
+// watched: coefficients the threshold killed INSIDE the guard band (watch mode): recorded with bit 31 set.
 template <int E>
-__device__ __forceinline__ void record_support(const BandArgs<float>& A, const int s, const unsigned (&idx)[E], const unsigned kept, int* sh) {
-    if (!__syncthreads_or(kept != 0u)) return;
-    const int cnt = __popc(kept);
+__device__ __forceinline__ void record_support(const BandArgs<float>& A, const int s, const unsigned (&idx)[E], const unsigned kept, int* sh,
+                                               const unsigned watched = 0u) {
+    const unsigned both = kept | watched;
+    if (!__syncthreads_or(both != 0u)) return;
+    if (watched) A.wflag[s] = 1;
+    const int cnt = __popc(both);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     int incl = cnt;
 #pragma unroll
@@ -167,13 +174,14 @@ __device__ __forceinline__ void record_support(const BandArgs<float>& A, const i
     unsigned* dst = A.arena + (long long)s * A.arena_cap + base + sh[w] + incl - cnt;
     int o = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) if ((kept >> e) & 1u) dst[o++] = idx[e];
+    for (int e = 0; e < E; ++e) if ((both >> e) & 1u) dst[o++] = idx[e] | (((watched >> e) & 1u) << 31);
 }
 // Guard band of the escalating-precision mode: |X| within g of Re(tau_k) means that the decision of this or of a
 // later iteration may depend on fp32 rounding.  Tested on |X|^2 (two compares per coefficient).
 template <typename T> struct GuardBand {
     T lo2, hi2;
     bool on, hit;
+    unsigned bits = 0u;          // bit e: element e is inside the band
     // centre = the modulus at which the operator jumps: Re(tau) for hard and soft, sqrt(Re(tau^2)) for garrote
     __device__ __forceinline__ GuardBand(const BandArgs<T>& A, const int s, const T a, const T b, const int op) {
         on = (sizeof(T) == 4) && (A.guard != nullptr);
@@ -186,10 +194,13 @@ template <typename T> struct GuardBand {
             if (hi > T(0)) { hi2 = hi * hi; lo2 = lo > T(0) ? lo * lo : T(-1); }
         }
     }
-    __device__ __forceinline__ void test(const Cx<T> v) {
+    __device__ __forceinline__ void test(const Cx<T> v, const int e = 0) {
         const T r2 = v.x * v.x + v.y * v.y;
-        hit |= (r2 > lo2) && (r2 < hi2);
+        const bool in = (r2 > lo2) && (r2 < hi2);
+        hit |= in;
+        bits |= in ? (1u << e) : 0u;
     }
+    // freeze on a hit (kernels without a watch list, or watch mode off)
     __device__ __forceinline__ void commit(const BandArgs<T>& A, const int s) const {
         if (on && hit) A.esc[s] = A.k + 1;       // every writer of this launch stores the same value
     }

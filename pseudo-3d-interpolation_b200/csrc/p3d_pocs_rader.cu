@@ -127,13 +127,14 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     // ---- threshold (or kx-ky filter) in Rader order
     const float a = tau.x, b = tau.y;
     const float t2re = a * a - b * b, t2im = 2.f * a * b;
+    unsigned nearbits = 0u;
     if (A.guard && op != P3D_OP_FILTER) {
         GuardBand<float> gb(A, s, a, b, op);
 #pragma unroll
-        for (int e = 0; e < E; ++e) gb.test(v[e]);
-        if (j == 0) gb.test(dc);
-        if (!ok) gb.hit = false;
-        gb.commit(A, s);
+        for (int e = 0; e < E; ++e) gb.test(v[e], e);
+        if (j == 0) gb.test(dc, E);
+        if (!ok) { gb.hit = false; gb.bits = 0u; }
+        if (A.watch) nearbits = gb.bits; else gb.commit(A, s);
     }
     if (op == P3D_OP_HARD && !A.exact_tie) {
 #pragma unroll
@@ -173,7 +174,7 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
         }
         idx[E] = (unsigned)col;
         if (ok && j == 0 && (dc.x != 0.f || dc.y != 0.f)) kept |= 1u << E;
-        record_support<E + 1>(A, s, idx, kept, rec_sh);
+        record_support<E + 1>(A, s, idx, kept, rec_sh, nearbits & ~kept);
     }
 
     // ---- inverse DFT of length P (unscaled): h[m] = Y[g^-m] is already in natural order of m

@@ -108,12 +108,13 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
 
     const F a = tau.x, b = tau.y;
     const F t2re = a * a - b * b, t2im = F(2) * a * b;
+    unsigned nearbits = 0u;
     if (sizeof(F) == 4 && A.guard && op != P3D_OP_FILTER) {
         GuardBand<F> gb(A, s, a, b, op);
 #pragma unroll
-        for (int e = 0; e < E; ++e) gb.test(v[e]);
-        if (!ok) gb.hit = false;
-        gb.commit(A, s);
+        for (int e = 0; e < E; ++e) gb.test(v[e], e);
+        if (!ok) { gb.hit = false; gb.bits = 0u; }
+        if (A.watch) nearbits = gb.bits; else gb.commit(A, s);
     }
     if (op == P3D_OP_HARD && !A.exact_tie) {
 #pragma unroll
@@ -142,7 +143,7 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
             idx[e] = ((unsigned)(j + e * T) << 16) | (unsigned)col;
             if (ok && (v[e].x != F(0) || v[e].y != F(0))) kept |= 1u << e;
         }
-        record_support<E>(reinterpret_cast<const BandArgs<float>&>(A), s, idx, kept, rec_sh);
+        record_support<E>(reinterpret_cast<const BandArgs<float>&>(A), s, idx, kept, rec_sh, nearbits & ~kept);
     }
 
     LP::template fft<+1, (LP::NEXCH & 1), F>(v, acc, j, tw);

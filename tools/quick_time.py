@@ -44,6 +44,8 @@ def main():
         plan.set_option("spec_variant64", int(a[10]))
     if os.environ.get("P3D_GUARD"):
         plan.set_option("guard_factor", int(float(os.environ["P3D_GUARD"])))
+    for kv in filter(None, os.environ.get("P3D_OPTS", "").split(",")):
+        plan.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     print(plan.describe())
     dx = _lib.DeviceBuffer(x.nbytes); dx.upload(x)
     dm = _lib.DeviceBuffer(mask.nbytes); dm.upload(mask)

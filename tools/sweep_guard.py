@@ -2,7 +2,7 @@
 
     python tools/sweep_guard.py CONFIG N_SLICES GUARDS [SEG] [NOISE]
 """
-import sys, time, json
+import os, sys, time, json
 import numpy as np
 import torch
 sys.path.insert(0, ".")
@@ -28,6 +28,8 @@ def run(prec, guard=None):
     plan = p3d.PocsPlan(n1, n2, precision=prec)
     if guard is not None:
         plan.set_option("guard_factor", guard); plan.set_option("seg_iters", seg)
+        for kv in filter(None, os.environ.get("P3D_OPTS", "").split(",")):
+            plan.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     out = torch.empty_like(x)
     plan.run_device(x.data_ptr(), mask.data_ptr(), out.data_ptr(), ns, params)
     plan.event_record(0)
