@@ -150,6 +150,7 @@ SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant) {
             else if (variant == 8) { P3D_COLS64(LP1000, 4, 2, "spec64<1000,E10,10x10x10,C4,2cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000, 4, 2, true, double, true>; }
             else if (variant == 9) { P3D_COLS64(LP1000, 2, 4, "spec64<1000,E10,10x10x10,C2,4cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000, 2, 4, true, double, true>; }
             else if (variant == 10) { P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta,cp.async,1buf>"); k.cols_iter = launch_cols<LP1000, 2, 3, true, double, true>; }
+            else if (variant == 11) { P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 2, 3, true, double>; }
             else { P3D_COLS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,C2,3cta,cp.async>"); k.cols_iter = launch_cols<LP1000, 2, 3, true, double>; }
             break;
         case 2000:
@@ -173,7 +174,9 @@ SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant) {
             else if (variant == 8) P3D_ROWS64(LP1000, 2, 3, "spec64<1000,E10,10x10x10,RB2,3cta>");
             else if (variant == 9) P3D_ROWS64(LP1000, 3, 2, "spec64<1000,E10,10x10x10,RB3,2cta>");
             else if (variant == 10) P3D_ROWS64(LP1000, 4, 1, "spec64<1000,E10,10x10x10,RB4,1cta>");
-            else              P3D_ROWS64(LP1000, 1, 4, "spec64<1000,E10,10x10x10,RB1,4cta>");
+            else if (variant == 11) { P3D_ROWS64(LP1000, 1, 4, "spec64<1000,E10,10x10x10,RB1,4cta,l2prefetch>"); k.rows_iter_io32 = launch_rows<LP1000, 1, 4, true, double, true>; }
+            else if (variant == 12) P3D_ROWS64(LP1000, 1, 4, "spec64<1000,E10,10x10x10,RB1,4cta>");
+            else { P3D_ROWS64(LP1000, 1, 4, "spec64<1000,E10,10x10x10,RB1,4cta,l2prefetch>"); k.rows_iter_io32 = launch_rows<LP1000, 1, 4, true, double, true>; }
             break;
         case 2000:
             if (variant == 1 || variant == 2) P3D_ROWS64(LP2000, 1, 2, "spec64<2000,E10,10x10x10x2,RB1,2cta>");
