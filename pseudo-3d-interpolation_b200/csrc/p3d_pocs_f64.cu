@@ -46,7 +46,12 @@ void f64_install_spec(F64Runner* R, int variant) {
         P3D_CUDA(cudaMalloc(dst, sizeof(Cx<double>) * t.size()));
         P3D_CUDA(cudaMemcpy(*dst, t.data(), sizeof(Cx<double>) * t.size(), cudaMemcpyHostToDevice));
     };
-    upload(R->spec.cols_radices, &R->tw_cols);
+    if (R->spec.cols_table) {
+        if (R->tw_cols) { cudaFree(R->tw_cols); R->tw_cols = nullptr; }
+        std::vector<Cx<double>> t = R->spec.cols_table();
+        P3D_CUDA(cudaMalloc(&R->tw_cols, sizeof(Cx<double>) * t.size()));
+        P3D_CUDA(cudaMemcpy(R->tw_cols, t.data(), sizeof(Cx<double>) * t.size(), cudaMemcpyHostToDevice));
+    } else upload(R->spec.cols_radices, &R->tw_cols);
     upload(R->spec.rows_radices, &R->tw_rows);
     R->mbits_words = 0;
 }

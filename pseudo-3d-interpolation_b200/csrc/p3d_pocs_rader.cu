@@ -29,18 +29,25 @@ __device__ __forceinline__ Cx<float> ldg_cx(const Cx<float>* p) {
     const float2 t = __ldg(reinterpret_cast<const float2*>(p));
     return cmake<float>(t.x, t.y);
 }
+__device__ __forceinline__ Cx<double> ldg_cx(const Cx<double>* p) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    return cmake<double>(t.x, t.y);
+}
 
 // MODE 0: statistics of X0 (+ optional store), MODE 1: iterate (threshold / filter)
 // BULK: tile load with cp.async.cg into exchange buffer 1 (see k_cols_spec), the row permutation applied to the SOURCE row
-template <typename MP, int P, int C, int MINB, int MODE, bool BULK>
+// F = double (complex128 state of the escalating / float64 modes): MODE 0 leaves the exact statistics (per-CTA lexicographic
+// maxima in A.cand) and, with A.store_x0_inplace, X0 in natural order in W; op = P3D_OP_RESTART takes a thresholded
+// spectrum in natural order and runs the inverse half only.
+template <typename F, typename MP, int P, int C, int MINB, int MODE, bool BULK>
 __global__ void __launch_bounds__(MP::T* C, MINB)
-k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tab, const __grid_constant__ BandArgs<float> A, const int op) {
+k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tab, const __grid_constant__ BandArgs<F> A, const int op) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int E = MP::E, T = MP::T, M = MP::N;
     static_assert(M == P - 1, "Rader: the convolution length is P - 1");
-    const Cx<float>* __restrict__ tw = tab;
-    const Cx<float>* __restrict__ Bf = tab + (T + M);
-    const Cx<float>* __restrict__ Bi = Bf + M;
+    const Cx<F>* __restrict__ tw = tab;
+    const Cx<F>* __restrict__ Bf = tab + (T + M);
+    const Cx<F>* __restrict__ Bi = Bf + M;
     const int* __restrict__ perm = reinterpret_cast<const int*>(Bi + M);
     const int* __restrict__ kperm = perm + M;
     const int s = band_slice(A);
@@ -48,62 +55,95 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     const int c = tid % C, j = tid / C;
     const int col = blockIdx.x * C + c;
     const bool ok = col < G.n2;
-    Cx<float>* __restrict__ Ws = A.W + (long long)s * P * G.n2 + col;
-    ColAcc<float, C, MP::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw) + c;
+    Cx<F>* __restrict__ Ws = A.W + (long long)s * P * G.n2 + col;
+    ColAcc<F, C, MP::LINE> acc; acc.base = reinterpret_cast<Cx<F>*>(smem_raw) + c;
 
+    const bool restart = (MODE == 1) && (sizeof(F) == 8) && (op == P3D_OP_RESTART);
     int row[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) row[e] = __ldg(perm + j + e * T);
-    Cx<float> v[E];
-    constexpr int CHUNKS = (C * (int)sizeof(Cx<float>)) / 16;
-    const bool bulk = BULK && (CHUNKS >= 1) && (blockIdx.x * C + C <= G.n2) && (((long long)G.n2 * sizeof(Cx<float>)) % 16 == 0) &&
+    Cx<F> v[E];
+    constexpr int CHUNKS = (C * (int)sizeof(Cx<F>)) / 16;
+    const bool bulk = BULK && (CHUNKS >= 1) && (blockIdx.x * C + C <= G.n2) && (((long long)G.n2 * sizeof(Cx<F>)) % 16 == 0) &&
                       ((reinterpret_cast<uintptr_t>(A.W) % 16) == 0);
     if (bulk) {
         const char* src0 = reinterpret_cast<const char*>(A.W + (long long)s * P * G.n2 + blockIdx.x * C);
-        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(reinterpret_cast<Cx<float>*>(smem_raw) + (size_t)MP::LINE * C);
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(reinterpret_cast<Cx<F>*>(smem_raw) + (size_t)MP::LINE * C);
         for (int q = tid; q < M * CHUNKS; q += T * C) {
             const int m = q / CHUNKS, part = q - m * CHUNKS;
-            const char* src = src0 + (long long)__ldg(perm + m) * G.n2 * sizeof(Cx<float>) + part * 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (unsigned)(m * C * sizeof(Cx<float>) + part * 16)), "l"(src));
+            const char* src = src0 + (long long)__ldg((restart ? kperm : perm) + m) * G.n2 * sizeof(Cx<F>) + part * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (unsigned)(m * C * sizeof(Cx<F>) + part * 16)), "l"(src));
         }
         asm volatile("cp.async.commit_group;");
     } else {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)row[e] * G.n2] : cmake<float>(0.f, 0.f);
+        for (int e = 0; e < E; ++e) v[e] = ok ? Ws[(long long)(restart ? __ldg(kperm + j + e * T) : row[e]) * G.n2] : cmake<F>(F(0), F(0));
     }
-    Cx<float> dc = (ok && j == 0) ? Ws[0] : cmake<float>(0.f, 0.f);
-    Cx<float> tau = cmake<float>(0.f, 0.f);
+    Cx<F> dc = (ok && j == 0) ? Ws[0] : cmake<F>(F(0), F(0));
+    Cx<F> tau = cmake<F>(F(0), F(0));
     if (MODE == 1) {
         tau = A.tau[(long long)s * A.niter + A.k];
-        if (slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps) || slice_escalated(A, s)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
+        if ((!A.restart && slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) || slice_escalated(A, s)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
     }
     if (bulk) {
         asm volatile("cp.async.wait_all;");
         __syncthreads();
-        const Cx<float>* land = acc.line(1);
+        const Cx<F>* land = acc.line(1);
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = land[(j + e * T) * C];
     }
 
-    // ---- forward DFT of length P
-    MP::template fft<-1, 0, float>(v, acc, j, tw);
-    {
-        const Cx<float> x0 = dc;
-        if (j == 0) dc = cadd(x0, v[0]);                 // X[0] = x[0] + sum_q a[q]
+    // ---- forward DFT of length P (not for a restart: the tile holds the thresholded spectrum, loaded in Rader order)
+    if (!restart) {
+        MP::template fft<-1, 0, F>(v, acc, j, tw);
+        {
+            const Cx<F> x0 = dc;
+            if (j == 0) dc = cadd(x0, v[0]);                 // X[0] = x[0] + sum_q a[q]
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], ldg_cx(Bf + j + e * T));
-        if (j == 0) v[0] = cadd(v[0], x0);               // + x[0] on every convolution output
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], ldg_cx(Bf + j + e * T));
+            if (j == 0) v[0] = cadd(v[0], x0);               // + x[0] on every convolution output
+        }
+        MP::template fft<+1, 0, F>(v, acc, j, tw);
     }
-    MP::template fft<+1, 0, float>(v, acc, j, tw);
     // v[e] = X[kperm[j + e*T]], dc = X[0] (threads j == 0)
 
+    if (MODE == 0 && sizeof(F) == 8) {
+        double bre = -INFINITY, bim = -INFINITY, ss = 0.0;
+        unsigned long long ak = 0ull, ik = ~0ull;
+        Cx<F>* __restrict__ Wo = A.W + (long long)s * P * G.n2 + col;
+        auto account = [&](const Cx<F> x, const int frow) {
+            if ((double)x.x > bre || ((double)x.x == bre && (double)x.y > bim)) { bre = (double)x.x; bim = (double)x.y; }
+            const double r2 = (double)x.x * (double)x.x + (double)x.y * (double)x.y;
+            ss += r2;
+            const unsigned long long k2 = f64_ordered(sqrt(r2));
+            ak = k2 > ak ? k2 : ak; ik = k2 < ik ? k2 : ik;
+            if (A.store_x0_inplace) Wo[(long long)frow * G.n2] = x;
+        };
+        if (ok) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) account(v[e], __ldg(kperm + j + e * T));
+            if (j == 0) account(dc, 0);
+        }
+        ss = warp_sum(ss); ak = warp_max_u64(ak);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long w2 = __shfl_xor_sync(0xffffffffu, ik, o); ik = w2 < ik ? w2 : ik; }
+        if ((tid & 31) == 0) {
+            atomicAdd(&A.stats[s].sumsq, ss);
+            atomicMax(&A.stats[s].maxabs64_key, ak);
+            atomicMin(&A.stats[s].minabs64_key, ik);
+        }
+        __syncthreads();
+        block_lexmax(bre, bim, reinterpret_cast<double*>(smem_raw));
+        if (tid == 0 && A.cand) A.cand[(long long)s * A.cand_stride + blockIdx.x] = make_double2(bre, bim);
+        return;
+    }
     if (MODE == 0) {
         unsigned long long kmax = 0ull; float ssf = 0.f; unsigned int amax = 0u, amin = 0xffffffffu;
-        Cx<float>* __restrict__ X0 = A.OUT + (long long)s * P * G.n2 + col;
-        auto account = [&](const Cx<float> x, const int frow) {
-            const unsigned long long key = lex_key(x.x, x.y);
+        Cx<F>* __restrict__ X0 = A.OUT + (long long)s * P * G.n2 + col;
+        auto account = [&](const Cx<F> x, const int frow) {
+            const unsigned long long key = lex_key((float)x.x, (float)x.y);
             kmax = key > kmax ? key : kmax;
-            const float r2 = x.x * x.x + x.y * x.y;
+            const float r2 = (float)(x.x * x.x + x.y * x.y);
             ssf += r2;
             const unsigned int rb = __float_as_uint(sqrtf(r2));
             amax = rb > amax ? rb : amax; amin = rb < amin ? rb : amin;
@@ -125,11 +165,11 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     }
 
     // ---- threshold (or kx-ky filter) in Rader order
-    const float a = tau.x, b = tau.y;
-    const float t2re = a * a - b * b, t2im = 2.f * a * b;
+    const F a = tau.x, b = tau.y;
+    const F t2re = a * a - b * b, t2im = F(2) * a * b;
     unsigned nearbits = 0u;
-    if (A.guard && op != P3D_OP_FILTER) {
-        GuardBand<float> gb(A, s, a, b, op);
+    if (sizeof(F) == 4 && A.guard && op != P3D_OP_FILTER) {
+        GuardBand<F> gb(A, s, a, b, op);
 #pragma unroll
         for (int e = 0; e < E; ++e) gb.test(v[e], e);
         if (j == 0) gb.test(dc, E);
@@ -138,55 +178,55 @@ k_cols_rader(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ t
     }
     if (op == P3D_OP_HARD && !A.exact_tie) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float, false>(v[e], a, b, t2re, t2im);
-        dc = apply_threshold<P3D_OP_HARD, float, false>(dc, a, b, t2re, t2im);
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, F, false>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_HARD, F, false>(dc, a, b, t2re, t2im);
     } else if (op == P3D_OP_HARD) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, float>(v[e], a, b, t2re, t2im);
-        dc = apply_threshold<P3D_OP_HARD, float>(dc, a, b, t2re, t2im);
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_HARD, F>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_HARD, F>(dc, a, b, t2re, t2im);
     } else if (op == P3D_OP_SOFT) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_SOFT, float>(v[e], a, b, t2re, t2im);
-        dc = apply_threshold<P3D_OP_SOFT, float>(dc, a, b, t2re, t2im);
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_SOFT, F>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_SOFT, F>(dc, a, b, t2re, t2im);
     } else if (op == P3D_OP_GARROTE) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_GARROTE, float>(v[e], a, b, t2re, t2im);
-        dc = apply_threshold<P3D_OP_GARROTE, float>(dc, a, b, t2re, t2im);
-    } else {
+        for (int e = 0; e < E; ++e) v[e] = apply_threshold<P3D_OP_GARROTE, F>(v[e], a, b, t2re, t2im);
+        dc = apply_threshold<P3D_OP_GARROTE, F>(dc, a, b, t2re, t2im);
+    } else if (op == P3D_OP_FILTER) {
         const float* __restrict__ H = A.filt + col;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const float h = ok ? __ldg(H + (long long)__ldg(kperm + j + e * T) * G.n2) : 0.f;
-            v[e] = cmake<float>(v[e].x * h, v[e].y * h);
+            const F h = ok ? (F)__ldg(H + (long long)__ldg(kperm + j + e * T) * G.n2) : F(0);
+            v[e] = cmake<F>(v[e].x * h, v[e].y * h);
         }
-        const float h0 = (ok && j == 0) ? __ldg(H) : 0.f;
-        dc = cmake<float>(dc.x * h0, dc.y * h0);
+        const F h0 = (ok && j == 0) ? (F)__ldg(H) : F(0);
+        dc = cmake<F>(dc.x * h0, dc.y * h0);
     }
 
-    if (A.arena && op != P3D_OP_FILTER) {
+    if (sizeof(F) == 4 && A.arena && op != P3D_OP_FILTER) {
         // support record of the fp32 pilot (exact restart): natural frequency row of every surviving coefficient
         __shared__ int rec_sh[34];
         unsigned idx[E + 1]; unsigned kept = 0u;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             idx[e] = ((unsigned)__ldg(kperm + j + e * T) << 16) | (unsigned)col;
-            if (ok && (v[e].x != 0.f || v[e].y != 0.f)) kept |= 1u << e;
+            if (ok && (v[e].x != F(0) || v[e].y != F(0))) kept |= 1u << e;
         }
         idx[E] = (unsigned)col;
-        if (ok && j == 0 && (dc.x != 0.f || dc.y != 0.f)) kept |= 1u << E;
-        record_support<E + 1>(A, s, idx, kept, rec_sh, nearbits & ~kept);
+        if (ok && j == 0 && (dc.x != F(0) || dc.y != F(0))) kept |= 1u << E;
+        record_support<E + 1>(reinterpret_cast<const BandArgs<float>&>(A), s, idx, kept, rec_sh, nearbits & ~kept);
     }
 
     // ---- inverse DFT of length P (unscaled): h[m] = Y[g^-m] is already in natural order of m
-    MP::template fft<-1, 0, float>(v, acc, j, tw);
+    MP::template fft<-1, 0, F>(v, acc, j, tw);
     {
-        const Cx<float> y0 = dc;
+        const Cx<F> y0 = dc;
         if (j == 0) dc = cadd(y0, v[0]);                 // y[0] = sum_k Y[k]
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = cmul(v[e], ldg_cx(Bi + j + e * T));
         if (j == 0) v[0] = cadd(v[0], y0);
     }
-    MP::template fft<+1, 0, float>(v, acc, j, tw);
+    MP::template fft<+1, 0, F>(v, acc, j, tw);
     // v[e] = y[g^(j + e*T)] = y[row[e]]
 
     if (ok) {
@@ -213,10 +253,13 @@ static int primitive_root(int p) {
 
 // ROWS = false: kernels of the column pass (forward DFT first: B = FFT(w^(g^-t)), B2 = FFT(conj(w)^(g^t)));
 // ROWS = true: kernels of the row pass (inverse DFT first: B = FFT(conj(w)^(g^-t)), B2 = FFT(w^(g^t)))
-template <typename MP, int P, bool ROWS = false> static std::vector<Cx<float>> rader_tables() {
+static std::vector<Cx<float>> twiddles_of(const std::vector<int>& r, float) { return spec_twiddle_table(r); }
+static std::vector<Cx<double>> twiddles_of(const std::vector<int>& r, double) { return spec_twiddle_table64(r); }
+
+template <typename MP, int P, bool ROWS = false, typename F = float> static std::vector<Cx<F>> rader_tables() {
     constexpr int M = P - 1;
     int rad[3]; MP::radices(rad);
-    std::vector<Cx<float>> t = spec_twiddle_table(std::vector<int>(rad, rad + 3));
+    std::vector<Cx<F>> t = twiddles_of(std::vector<int>(rad, rad + 3), F(0));
     static_assert(MP::T % 2 == 0, "Rader table offsets assume an even pass-2 table");
     t.resize((size_t)MP::T + M);                                    // exact size of the twiddle section
     const int g = primitive_root(P);
@@ -239,10 +282,10 @@ template <typename MP, int P, bool ROWS = false> static std::vector<Cx<float>> r
             cd acc(0, 0);
             for (int q = 0; q < M; ++q) acc += src[q] * wM[(int)(((long)k * q) % M)];
             acc /= (double)M;
-            t.push_back(cmake<float>((float)acc.real(), (float)acc.imag()));
+            t.push_back(cmake<F>((F)acc.real(), (F)acc.imag()));
         }
     }
-    const size_t int_slots = (size_t)M;                            // 2 * M ints = M Cx<float> slots
+    const size_t int_slots = ((size_t)2 * M * sizeof(int) + sizeof(Cx<F>) - 1) / sizeof(Cx<F>);      // 2 * M ints
     const size_t base = t.size();
     t.resize(base + int_slots);
     int* ip = reinterpret_cast<int*>(t.data() + base);
@@ -251,16 +294,20 @@ template <typename MP, int P, bool ROWS = false> static std::vector<Cx<float>> r
     return t;
 }
 
-template <typename MP, int P, int C, int MINB, int MODE, bool BULK = false>
-static void launch_rader(const PocsGeom& G, const Cx<float>* tab, const BandArgs<float>& A, int ns, int op, cudaStream_t st) {
-    constexpr size_t smem = (size_t)2 * MP::LINE * C * sizeof(Cx<float>);
+template <typename MP, int P, int C, int MINB, int MODE, bool BULK = false, typename F = float>
+static void launch_rader(const PocsGeom& G, const Cx<F>* tab, const BandArgs<F>& A, int ns, int op, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * MP::LINE * C * sizeof(Cx<F>);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_cols_rader<MP, P, C, MINB, MODE, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cols_rader<F, MP, P, C, MINB, MODE, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     dim3 grid((G.n2 + C - 1) / C, ns);
-    k_cols_rader<MP, P, C, MINB, MODE, BULK><<<grid, MP::T * C, smem, st>>>(G, tab, A, op);
+    k_cols_rader<F, MP, P, C, MINB, MODE, BULK><<<grid, MP::T * C, smem, st>>>(G, tab, A, op);
+}
+template <typename MP, int P, int C, int MINB>
+static void launch_rader_stats64(const PocsGeom& G, const Cx<double>* tab, const BandArgs<double>& A, int ns, cudaStream_t st) {
+    launch_rader<MP, P, C, MINB, 0, false, double>(G, tab, A, ns, 0, st);
 }
 template <typename MP, int P, int C, int MINB>
 static void launch_rader_stats(const PocsGeom& G, const Cx<float>* tab, const BandArgs<float>& A, int ns, cudaStream_t st) {
@@ -396,6 +443,18 @@ void rader_register_rows(SpecKernels& k, int n_xline, int variant) {
         k.rows_table = rader_tables<MP1200, 1201, true>;
     }
     k.rows_init = nullptr; k.pack_mask = nullptr; k.rows_T = 0;       // generic row FFT of the observed slice, byte mask
+}
+
+// complex128 state (escalating / float64 modes): the same algorithm over 10 x 12 x 10 (E = 10: 40 data registers)
+void rader_register_cols64(SpecKernels64& k, int n_iline, int variant) {
+    if (n_iline != 1201) return;
+    (void)variant;
+    k.cols_iter = launch_rader<MP1200, 1201, 2, 2, 1, false, double>;
+    k.cols_stats = launch_rader_stats64<MP1200, 1201, 2, 2>;
+    k.cols_C = 2;
+    k.cols_name = "rader64<1201,10x12x10,C2,2cta>";
+    k.cols_radices = {10, 12, 10};
+    k.cols_table = rader_tables<MP1200, 1201, false, double>;
 }
 
 void rader_register_cols(SpecKernels& k, int n_iline, int variant) {

@@ -164,7 +164,7 @@ SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant) {
         case 256:  P3D_COLS64(LP256E8, 8, 3, "spec64<256,E8,8x8x4,C8>"); break;
         case 200:  P3D_COLS64(LP200E10, 8, 4, "spec64<200,E10,10x10x2,C8>"); break;
         case 847:  P3D_COLS64(MP847, 2, 3, "mix64<847,11x7x11,C2,3cta>"); break;
-        default: break;
+        default: rader_register_cols64(k, n_iline, variant); break;
     }
     switch (n_xline) {
         case 1000:

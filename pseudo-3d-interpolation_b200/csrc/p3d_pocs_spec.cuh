@@ -61,7 +61,9 @@ struct SpecKernels64 {
     const char* rows_name = "generic64";
     std::vector<int> cols_radices, rows_radices;
     int rows_T = 0;
+    std::vector<Cx<double>> (*cols_table)() = nullptr;   // whole table buffer of the column kernels (Rader) instead of plain twiddles
 };
+void rader_register_cols64(SpecKernels64& k, int n_iline, int variant);
 SpecKernels64 select_spec_kernels64(int n_iline, int n_xline, int variant = 0);
 std::vector<Cx<double>> spec_twiddle_table64(const std::vector<int>& radices);
 

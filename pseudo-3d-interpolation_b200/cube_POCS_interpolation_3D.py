@@ -11,6 +11,12 @@ p_max, p_min, sqrt_decay, decay_kind, version}``, ``output_runtime_results``; th
 accepted and ignored: the slice loop of cube_POCS_interpolation_3D.py:303-340 is replaced by
 contiguous frequency bands over the visible GPUs (``n_gpus`` key or all of them).
 
+Extensions (not in the reference): the YAML key ``precision`` ("auto" = escalating fp32 -> complex128, the default;
+32; 64) and the flag ``--fused``: ``path_cube`` is then the TIME-domain cube of step 11 and steps 12 -> 13 -> 14 run
+chained on the device (``pipeline.interpolate_time_cube`` / ``distributed.interpolate_time_cube_distributed``
+under torchrun): one upload, no frequency-domain files; ``--compute_real`` as in steps 12 / 14.  The output is the
+interpolated time cube ``{file}_interp{suffix}`` (variable ``<var>_interp``), as step 14 would write it.
+
 Outputs follow the reference's names: directory ``{file}_{TRANSFORM}_{thresh_op}_niter-{niter}``
 with ``parameter_{prefix}.yml`` (and ``runtimes_{prefix}.txt``), and the merged cube
 ``{out_dir}{suffix}`` whose frequency axis is ascending like the reference's
@@ -43,6 +49,11 @@ def define_input_args():  # noqa
     parser.add_argument("--path_output_dir", type=str, help="Output directory for interpolated slices.")
     parser.add_argument("--verbose", "-V", type=int, nargs="?", default=0, choices=[0, 1, 2],
                         help="Level of output verbosity (default: 0)")
+    # extension: steps 12 -> 13 -> 14 chained on the device, from and to the time-domain cube
+    parser.add_argument("--fused", action="store_true",
+                        help="path_cube is the time-domain cube: apply FFT, POCS and IFFT on the GPU without intermediate files.")
+    parser.add_argument("--compute_real", action="store_true",
+                        help="(with --fused) transform assuming real input, discarding the redundant negative frequencies.")
     return parser
 
 
@@ -76,7 +87,7 @@ def interpolate(cube: Cube, cfg: dict, devices=None, verbose=0):
         devices = list(range(min(int(cfg.get("n_gpus", n)), n)))
     results = {}
     t0 = time.perf_counter()
-    out = pocs_cube(np.ascontiguousarray(data), mask, devices=devices, results=results, **metadata)
+    out = pocs_cube(np.ascontiguousarray(data), mask, devices=devices, results=results, precision=cfg.get("precision"), **metadata)
     runtime = time.perf_counter() - t0
     xprint(f"POCS on {len(devices)} GPU(s): {data.shape[0]} slices in {runtime:.2f} s", kind="info", verbosity=verbose)
 
@@ -104,10 +115,55 @@ def interpolate(cube: Cube, cfg: dict, devices=None, verbose=0):
     return res, info
 
 
+def interpolate_fused(cube: Cube, cfg: dict, compute_real=True, device=0, verbose=0):
+    """Steps 12 -> 13 -> 14 on the device for a time-domain cube -> (Cube with ``<var>_interp``, info)."""
+    from .pipeline import interpolate_time_cube
+    metadata = dict(cfg["metadata"])
+    metadata["transform_kind"] = str(metadata["transform_kind"]).upper()
+    if metadata["transform_kind"] != "FFT":
+        raise ValueError(f'Transform < {metadata["transform_kind"]} > is not supported.')
+    var = cfg.get("var") or [v for v in cube.data_vars if v != "fold"][0]
+    dims, data = cube.variables[var]
+    if "twt" not in dims:
+        raise ValueError("--fused needs the time-domain cube (dimension 'twt')")
+    if tuple(dims) != ("twt", "iline", "xline"):
+        data = np.transpose(data, [dims.index(d) for d in ("twt", "iline", "xline")])
+    fold = cube.data("fold")
+    if cube.dims_of("fold") == ("xline", "iline"):
+        fold = fold.T
+    results = {}
+    t0 = time.perf_counter()
+    out = interpolate_time_cube(np.ascontiguousarray(data, dtype=np.float32), np.asarray(cube.coords["twt"], dtype=np.float64), fold,
+                                compute_real=compute_real, device=device, precision=cfg.get("precision"), results=results, **metadata)
+    runtime = time.perf_counter() - t0
+    xprint(f"FFT -> POCS -> IFFT on the device: {len(results['niterations'])} slices in {runtime:.2f} s", kind="info", verbosity=verbose)
+    res = Cube(attrs=dict(cube.attrs), coord_attrs=dict(cube.coord_attrs), var_attrs=dict(cube.var_attrs))
+    res.coords = {k: np.asarray(v) for k, v in cube.coords.items()}
+    res.coords["twt"] = np.asarray(cube.coords["twt"])[: out.shape[0]]
+    res.variables[f"{var}_interp"] = (("twt", "iline", "xline"), out)
+    res.variables["fold"] = (("iline", "xline"), np.asarray(fold))
+    res.var_attrs[f"{var}_interp"] = dict(cube.var_attrs.get(var, {}))
+    script = os.path.basename(__file__)
+    res.attrs["history"] = cube.attrs.get("history", "") + f"{script}:FFT({var});{script}:FFT (frequency domain);{script}:IFFT({var}_interp);"
+    return res, dict(niterations=results["niterations"], cost=results["cost"], runtime=runtime)
+
+
 def main(argv=sys.argv, return_dataset=False):
     """Interpolate sparse 3D cube."""
     args = define_input_args().parse_args(argv[1:])
     verbose = args.verbose
+    if args.fused:
+        with open(args.path_pocs_parameter, mode="r") as f:
+            cfg = yaml.safe_load(f)
+        cube = open_cube(args.path_cube)
+        res, _ = interpolate_fused(cube, cfg, compute_real=args.compute_real, verbose=verbose)
+        base, suffix = os.path.splitext(args.path_cube)
+        out_dir = args.path_output_dir
+        out_file = os.path.join(out_dir, os.path.basename(base) + "_interp" + suffix) if out_dir else base + "_interp" + suffix
+        if out_dir and not os.path.isdir(out_dir):
+            os.mkdir(out_dir)
+        write_cube(out_file, res, split_complex=True)
+        return res if return_dataset else None
     xprint("Load POCS parameter from config file", kind="info", verbosity=verbose)
     with open(args.path_pocs_parameter, mode="r") as f:
         cfg = yaml.safe_load(f)

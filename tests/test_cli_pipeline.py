@@ -130,3 +130,31 @@ def test_on_device_chain_matches_oracle_chain(nt, compute_real):
     assert np.linalg.norm(spec - S_ref) / np.linalg.norm(S_ref) < 1e-4
     assert np.linalg.norm(y - x_ref) / np.linalg.norm(x_ref) < 1e-4
     assert np.all(res["niterations"][np.abs(F_ref).reshape(F_ref.shape[0], -1).max(axis=1) > 0] == 12)
+
+
+@pytest.mark.gpu
+def test_fused_cli_equals_three_step_chain(tmp_path):
+    """`13_cube_interpolate_POCS cube_twt --fused`: steps 12 -> 13 -> 14 chained on the device give the same time cube as the
+    three scripts with their intermediate files, and the YAML `precision` key is honoured."""
+    cube, _ = _time_cube(nt=128, n1=30, n2=26, seed=11)
+    p_time = str(tmp_path / "cube_twt.npz")
+    cube_io.write_cube(p_time, cube)
+    p_nc = str(tmp_path / "attrs.yml")
+    with open(p_nc, "w") as f:
+        yaml.safe_dump(dict(attrs_time=dict(env=dict(units="amp"), twt=dict(units="ms")), attrs_freq=dict(data=dict(units="-"), new_dim=dict(units="kHz"))), f)
+    meta = dict(transform_kind="fft", niter=14, eps=0.0, thresh_op="hard", thresh_model="exponential", alpha=1.0, p_max=0.99, p_min=1e-4)
+    for precision in ("auto", 64):
+        p_cfg = str(tmp_path / f"pocs_{precision}.yml")
+        with open(p_cfg, "w") as f:
+            yaml.safe_dump(dict(dim="freq_twt", var="freq_env", precision=precision, metadata=meta), f)
+        cube_apply_FFT.main(["12", p_time, "--params_netcdf", p_nc, "--compute_real"], return_dataset=True)
+        step13.main(["13", str(tmp_path / "cube_freq.npz"), "--path_pocs_parameter", p_cfg], return_dataset=True)
+        three = cube_apply_IFFT.main(["14", str(tmp_path / "cube_freq_FFT_hard_niter-14.npz"), "--params_netcdf", p_nc, "--compute_real"],
+                                     return_dataset=True).data("env")
+        with open(p_cfg, "w") as f:
+            yaml.safe_dump(dict(var="env", precision=precision, metadata=meta), f)
+        fused = step13.main(["13", p_time, "--path_pocs_parameter", p_cfg, "--fused", "--compute_real"], return_dataset=True)
+        assert os.path.exists(str(tmp_path / "cube_twt_interp.npz"))
+        y = fused.data("env_interp")
+        assert y.dtype == np.float32 and y.shape == three.shape
+        assert np.linalg.norm(y - three) / np.linalg.norm(three) < 1e-5
