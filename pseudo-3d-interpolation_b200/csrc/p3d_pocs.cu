@@ -73,6 +73,7 @@ struct p3d_plan {
     double guard_factor = 1024.0;    // guard half-width in units of eps32 * rms|X| (escalating mode)
     int seg_iters = 4;               // escalating mode: iterations between two compactions of the active-slice list
     int arena_cap = 16384;           // escalating mode: support-record entries per slice (all pilot iterations together)
+    int use_tma = 1;                 // column tiles fetched with cp.async.bulk.tensor where the tile shape allows it
     int watch_mode = -1;             // escalating mode: guard-band hits are verified by the float64 replay instead of freezing the slice
                                      // (-1 = where it pays: slices of 400 k points and more; small slices freeze on the first hit -
                                      // their replay launches cost more than the complex128 iterations they would save)
@@ -608,6 +609,7 @@ void process_chunk(RunCtx& R, Lane& L, int64_t first, int64_t count) {
         BandArgs<float> B = A;
         B.W = L.W + b0 * ne; B.D = D + b0 * ne; B.OUT = OUT + b0 * ne;
         B.first_slice = first + b0;
+        if (P->use_tma) { B.tma_base = L.W; B.tma_slices = L.cap; B.tma_slice0 = (int)b0; }
         B.tau = L.tau + b0 * niter; B.S = L.S + b0 * (niter + 1); B.stop = L.stop + b0; B.stats = L.stats + b0;
         return B;
     };
@@ -952,6 +954,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     A.W = L.W; A.D = D; A.OUT = OUT; A.first_slice = first; A.tau = L.tau; A.S = L.S; A.stop = L.stop; A.stats = L.stats;
     A.exact_tie = (pr.thresh_model == P3D_MODEL_INVERSE_PROPORTIONAL || data_driven || pr.decay_factors) ? 1 : 0;
     A.esc = L.esc;
+    if (P->use_tma) { A.tma_base = L.W; A.tma_slices = L.cap; A.tma_slice0 = 0; }
 
     BandArgs<double> A64;
     memset(&A64, 0, sizeof(A64));
@@ -959,6 +962,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     A64.inv_n = 1.0 / ((double)P->n1 * (double)P->n2);
     A64.W = L.W64; A64.D32 = D; A64.OUT32 = OUT; A64.first_slice = first; A64.tau = L.tau64; A64.S = L.S; A64.stop = L.stop;
     A64.stats = L.stats; A64.exact_tie = 1; A64.cand = L.cand; A64.cand_stride = L.cand_stride; A64.esc = L.esc;
+    if (P->use_tma) { A64.tma_base = L.W64; A64.tma_slices = L.cap; A64.tma_slice0 = 0; }
 
     // launch helpers over a (compacted) list of slices of this chunk
     auto rows_init64 = [&](BandArgs<double> B, const int* list, int n) {
@@ -1688,6 +1692,7 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     else if (!strcmp(key, "guard_factor")) P->guard_factor = (double)value;
     else if (!strcmp(key, "seg_iters")) P->seg_iters = (int)std::max<int64_t>(1, value);
     else if (!strcmp(key, "watch_mode")) P->watch_mode = (int)value;
+    else if (!strcmp(key, "use_tma")) P->use_tma = value != 0;
     else if (!strcmp(key, "support_cap")) P->support_cap = (int)std::max<int64_t>(0, value);
     else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(32768, std::max<int64_t>(128, value));
     else if (!strcmp(key, "spec_variant")) {

@@ -7,6 +7,7 @@
 // sum|d|) and k_cols_stats (column FFT + the statistics the schedule needs).
 #pragma once
 #include <stdint.h>
+#include <cuda.h>          // CUtensorMap (TMA descriptor of the work spectrum; no driver library is linked)
 #include "../../include/p3d_b200.h"
 #include "p3d_fft_generic.cuh"
 
@@ -110,7 +111,19 @@ template <typename T> struct BandArgs {
     int* wflag;                  // [band] set when a slice has recorded such a "watched kill"
     int restart;                 // complex128 kernels: this launch rebuilds x_{k_e - 1} (iteration index = esc[s] - 2 per slice)
     int store_x0_inplace;        // complex128 statistics kernel: leave X0 in W
+    // TMA descriptor of the lane's work array as a 3-D tensor (column, row, slice) with a box of C columns x tma_rows rows:
+    // the column kernels fetch their tile with cp.async.bulk.tensor instead of per-thread cp.async pieces
+    int use_tma;                 // set by the launcher when the tile shape allows it (see launch_cols)
+    int tma_rows;                // rows per box (divides n1, <= 256, box bytes a multiple of 128)
+    int tma_slice0;              // slice index of W inside the tensor
+    const void* tma_base;        // host request: base of the lane's work array and its slice capacity (null = no TMA)
+    long long tma_slices;
+    alignas(64) CUtensorMap tmapW;
 };
+
+// host: encode `map` for a (slices, n1, n2) array of complex values of `elem_bytes` bytes at `base`, box = C columns x
+// `rows` rows x 1 slice.  Returns false when the driver entry point is unavailable or rejects the shape.
+bool tma_encode_tile_map(CUtensorMap* map, const void* base, long long slices, int n1, int n2, int elem_bytes, int C, int rows);
 
 // internal operator of the complex128 column kernel: the tile already holds a thresholded spectrum (exact restart):
 // inverse transform only

@@ -41,6 +41,29 @@ __device__ __forceinline__ double norm_sqrt(double v) {
 template <typename LP> struct single_buffer_ok { static constexpr bool value = true; };
 template <int N, int Ra, int Rb> struct single_buffer_ok<MixPlan3<N, Ra, Rb>> { static constexpr bool value = MixPlan3<N, Ra, Rb>::SINGLE_BUFFER_OK; };
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -----------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");       // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// wait for phase `parity`; traps instead of hanging if the transfer never completes (bad descriptor)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- column kernel ---------------------------------------------------------------------------------
 // BULK: the tile is loaded with cp.async.cg (global -> shared memory in 16-byte pieces, no register and no L1 staging)
 // into exchange buffer 1, which is free until the second exchange, in the [row][c] layout of the accessor, and read
@@ -52,7 +75,7 @@ template <int N, int Ra, int Rb> struct single_buffer_ok<MixPlan3<N, Ra, Rb>> { 
 template <typename F, typename LP, int C, int MINB, bool BULK, bool SB = false>
 __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A, const int op) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     static_assert(!SB || single_buffer_ok<LP>::value, "this plan needs two exchange buffers");
     const int s = band_slice(A);
@@ -69,7 +92,21 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     // (uniform over the CTA) whole tile inside the slice, rows 16-byte aligned
     const bool bulk = BULK && (CHUNKS >= 1) && (blockIdx.x * C + C <= G.n2) && (((long long)G.n2 * sizeof(Cx<F>)) % 16 == 0) &&
                       ((reinterpret_cast<uintptr_t>(A.W) % 16) == 0);
-    if (bulk) {
+    // TMA: one thread fetches the tile as boxes of (C columns x tma_rows rows) of the 3-D tensor (column, row, slice);
+    // the transfer never touches the LSU pipe or a register, completion is an mbarrier transaction count
+    __shared__ __align__(8) unsigned long long tma_bar;
+    const bool tma = bulk && A.use_tma;
+    if (tma) {
+        if (tid == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&tma_bar, (unsigned)(N * C * sizeof(Cx<F>)));
+            Cx<F>* dst = reinterpret_cast<Cx<F>*>(smem_raw) + (SB ? (size_t)0 : (size_t)LP::LINE * C);
+            constexpr int PER = (int)(sizeof(Cx<F>) / 8);                   // tensor elements (8 bytes) per complex value
+            for (int r0 = 0; r0 < N; r0 += A.tma_rows)
+                tma_load_3d(dst + (size_t)r0 * C, &A.tmapW, (int)(blockIdx.x * C * PER), r0, A.tma_slice0 + s, &tma_bar);
+        }
+    } else if (bulk) {
         const char* src0 = reinterpret_cast<const char*>(A.W + (long long)s * N * G.n2 + blockIdx.x * C);
         const unsigned dst0 = (unsigned)__cvta_generic_to_shared(reinterpret_cast<Cx<F>*>(smem_raw) + (SB ? (size_t)0 : (size_t)LP::LINE * C));
         for (int q = tid; q < N * CHUNKS; q += T * C) {
@@ -85,10 +122,17 @@ k_cols_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
     const Cx<F> tau = A.tau[(long long)s * A.niter + A.k];
     // the (rare) early-exit test comes AFTER the loads were issued, so that its own dependent
     // loads (stop flag, two sums) do not delay them
-    if ((!A.restart && slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) || slice_escalated(A, s)) { if (bulk) asm volatile("cp.async.wait_all;"); return; }
-    if (bulk) {
+    if ((!A.restart && slice_stopped(A.stop, A.S, s, A.k, A.niter, A.eps)) || slice_escalated(A, s)) {
+        if (tma) mbar_wait(&tma_bar, 0); else if (bulk) asm volatile("cp.async.wait_all;");
+        return;
+    }
+    if (tma) {
+        mbar_wait(&tma_bar, 0);
+    } else if (bulk) {
         asm volatile("cp.async.wait_all;");
         __syncthreads();
+    }
+    if (bulk) {
         const Cx<F>* land = acc.line(1);
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = land[(j + e * T) * C];
@@ -170,7 +214,7 @@ template <typename F> struct IoSel<true, F> {
 template <typename F, typename LP, int RB, int MINB, bool PF, bool IO32 = false>
 __global__ void __launch_bounds__(LP::T* RB, MINB)
 k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red_s[32];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     static_assert(E <= 32, "mask bits are packed into one 32-bit word");
@@ -261,7 +305,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
 template <typename F, typename LP, int RB, int MINB>
 __global__ void __launch_bounds__(LP::T* RB, MINB)
 k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red_s[32];
     __shared__ unsigned long long red_n[32];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
@@ -335,7 +379,7 @@ k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ t
 template <typename LP, int C, int MINB>
 __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_stats_spec64(const __grid_constant__ PocsGeom G, const Cx<double>* __restrict__ tw, const __grid_constant__ BandArgs<double> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     const int s = band_slice(A);
     const int tid = threadIdx.x;
@@ -381,7 +425,7 @@ k_cols_stats_spec64(const __grid_constant__ PocsGeom G, const Cx<double>* __rest
 template <typename LP, int C, int MINB>
 __global__ void __launch_bounds__(LP::T* C, MINB)
 k_cols_stats_spec(const __grid_constant__ PocsGeom G, const Cx<float>* __restrict__ tw, const __grid_constant__ BandArgs<float> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int E = LP::E, T = LP::T, N = LP::N;
     const int s = band_slice(A);
     const int tid = threadIdx.x;
@@ -432,6 +476,12 @@ __global__ void k_pack_mask(const uint8_t* __restrict__ mask, uint32_t* __restri
 }
 
 // ---- registry ----------------------------------------------------------------------------------------
+// rows per TMA box: the largest divisor of N that is <= 256 and makes the box a multiple of 128 bytes (0 = none)
+constexpr int tma_box_rows(int N, int row_bytes) {
+    for (int r = 256; r >= 1; --r)
+        if (N % r == 0 && (r * row_bytes) % 128 == 0) return r;
+    return 0;
+}
 template <typename LP, int C, int MINB, bool BULK = false, typename F = float, bool SB = false>
 static void launch_cols(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A, int ns, int op, cudaStream_t st) {
     constexpr size_t smem = (size_t)(SB ? 1 : 2) * LP::LINE * C * sizeof(Cx<F>);
@@ -441,6 +491,29 @@ static void launch_cols(const PocsGeom& G, const Cx<F>* tw, const BandArgs<F>& A
         configured = true;
     }
     dim3 grid((G.n2 + C - 1) / C, ns);
+    // TMA tile load when the caller offers the lane's work array and the tile shape qualifies: boxes and the landing
+    // buffer 128-byte aligned, row segments of at least 16 bytes
+    constexpr int ROWS = tma_box_rows(LP::N, C * (int)sizeof(Cx<F>));
+    constexpr bool TMA_SHAPE = BULK && ROWS > 0 && (C * sizeof(Cx<F>)) % 16 == 0 && ((size_t)LP::LINE * C * sizeof(Cx<F>)) % 128 == 0;
+    if (TMA_SHAPE && A.tma_base) {
+        // one descriptor per (work array, capacity) and calling thread: lanes launch from their own threads
+        thread_local const void* cached_base = nullptr;
+        thread_local long long cached_slices = 0;
+        thread_local int cached_n2 = 0;
+        thread_local bool cached_ok = false;
+        thread_local BandArgs<F> B;
+        if (cached_base != A.tma_base || cached_slices != A.tma_slices || cached_n2 != G.n2) {
+            cached_ok = tma_encode_tile_map(&B.tmapW, A.tma_base, A.tma_slices, LP::N, G.n2, (int)sizeof(Cx<F>), C, ROWS);
+            cached_base = A.tma_base; cached_slices = A.tma_slices; cached_n2 = G.n2;
+        }
+        if (cached_ok) {
+            const CUtensorMap keep = B.tmapW;
+            B = A;
+            B.tmapW = keep; B.use_tma = 1; B.tma_rows = ROWS;
+            k_cols_spec<F, LP, C, MINB, BULK, SB><<<grid, LP::T * C, smem, st>>>(G, tw, B, op);
+            return;
+        }
+    }
     k_cols_spec<F, LP, C, MINB, BULK, SB><<<grid, LP::T * C, smem, st>>>(G, tw, A, op);
 }
 template <typename LP, int RB, int MINB, bool PF = false, typename F = float, bool IO32 = false>
