@@ -73,12 +73,16 @@ struct p3d_plan {
     double guard_factor = 1024.0;    // guard half-width in units of eps32 * rms|X| (escalating mode)
     int seg_iters = 4;               // escalating mode: iterations between two compactions of the active-slice list
     int arena_cap = 16384;           // escalating mode: support-record entries per slice (all pilot iterations together)
+    int64_t pilot_min_elems = 50000; // escalating mode: slices smaller than this run in complex128 from the first iteration (measured:
+                                     // 200 x 200 slices gain nothing from the pilot - its launches and the replay cost what it saves -
+                                     // 256 x 256 slices gain 13 %)
     int use_tma = 1;                 // column tiles fetched with cp.async.bulk.tensor where the tile shape allows it
     int watch_mode = -1;             // escalating mode: guard-band hits are verified by the float64 replay instead of freezing the slice
                                      // (-1 = where it pays: slices of 400 k points and more; small slices freeze on the first hit -
                                      // their replay launches cost more than the complex128 iterations they would save)
-    int support_cap = 0;             // escalating mode: largest support replayed per iteration (0 = 4 sqrt(n1 n2): where one more
-                                     // replayed iteration, ~|S|^2 gathers, costs what the complex128 iteration it replaces does)
+    int support_cap = 0;             // escalating mode: largest support replayed per iteration (0 = 2.2 sqrt(n1 n2): where one more
+                                     // replayed iteration, |S|^2 gathers at the measured 2.4 ps each, costs what the complex128
+                                     // iteration it replaces does, 11.7 us per 10^6 points more than an fp32 one)
     Cx<double>* mhat = nullptr; int64_t mhat_masks = 0;          // fft2 of the mask planes in complex128 (exact restart)
     Cx<float>* mask_c64 = nullptr; SliceStats* mh_stats = nullptr; double2* mh_cand = nullptr; int mh_cand_stride = 0;
     int64_t n_escalated = 0, n_esc_iters = 0;   // statistics of the last run (escalating mode)
@@ -1032,7 +1036,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     std::vector<cd> tau;
     const double eps32 = 5.9604644775390625e-08;      // 2^-24
     // adaptive POCS has no sparse recursion of this form: complex128 from the first iteration (an infinite guard band)
-    const double gfac = adaptive ? std::numeric_limits<double>::infinity() : P->guard_factor;
+    const double gfac = (adaptive || ne < P->pilot_min_elems) ? std::numeric_limits<double>::infinity() : P->guard_factor;
     auto store_tau = [&](int64_t i) {
         for (int k = 0; k < niter; ++k) {
             L.h_tau[i * niter + k] = cmake<float>((float)tau[k].real(), (float)tau[k].imag());
@@ -1142,7 +1146,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             B.guard = guard_on ? L.guard : nullptr;
             if (guard_on) {
                 B.arena = L.arena; B.acnt = L.acnt; B.astart = L.astart; B.arena_cap = acap;
-                B.scap = P->support_cap > 0 ? P->support_cap : (int)(4.0 * std::sqrt((double)ne));
+                B.scap = P->support_cap > 0 ? P->support_cap : (int)(2.2 * std::sqrt((double)ne));
                 // watch list (kernels that record the guard band; bit 31 of an entry must be free): a hit is verified by
                 // the replay instead of freezing the slice
                 const bool want_watch = P->watch_mode < 0 ? (ne >= 400000) : (P->watch_mode != 0);
@@ -1485,6 +1489,23 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
 
 }  // namespace
 
+// data-driven schedule from a complex128 X0 on the device (shared with the float64 state mode, p3d_pocs_f64.cu)
+namespace p3d {
+size_t dd_schedule64_temp_bytes(long long ne) {
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                              (unsigned int*)nullptr, (unsigned int*)nullptr, ne, 0, 64, (cudaStream_t)0);
+    return need;
+}
+void dd_schedule64_device(const Cx<double>* X0, long long ne, double lo_re, double lo_im, double hi_re, double hi_im, SliceStats* stats,
+                          Cx<double>* tau64, int niter, unsigned long long* keys, unsigned int* vals, void* temp, size_t temp_bytes,
+                          cudaStream_t st) {
+    k_dd_keys64<<<std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(X0, ne, lo_re, lo_im, hi_re, hi_im, keys, vals, stats);
+    cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, keys, keys + ne, vals, vals + ne, ne, 0, 64, st);
+    k_pick_tau64<<<1, 128, 0, st>>>(keys + ne, vals + ne, X0, stats, tau64, niter);
+}
+}  // namespace p3d
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -1693,6 +1714,7 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     else if (!strcmp(key, "seg_iters")) P->seg_iters = (int)std::max<int64_t>(1, value);
     else if (!strcmp(key, "watch_mode")) P->watch_mode = (int)value;
     else if (!strcmp(key, "use_tma")) P->use_tma = value != 0;
+    else if (!strcmp(key, "pilot_min_elems")) P->pilot_min_elems = value;
     else if (!strcmp(key, "support_cap")) P->support_cap = (int)std::max<int64_t>(0, value);
     else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(32768, std::max<int64_t>(128, value));
     else if (!strcmp(key, "spec_variant")) {

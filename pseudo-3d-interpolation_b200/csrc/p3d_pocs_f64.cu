@@ -27,6 +27,7 @@ struct F64Runner {
     Cx<double>* tw_cols = nullptr; Cx<double>* tw_rows = nullptr;
     uint32_t* mbits = nullptr; int64_t mbits_words = 0;
     int force_generic = 0;
+    unsigned long long* dd_keys = nullptr; unsigned int* dd_vals = nullptr; void* dd_temp = nullptr; size_t dd_temp_bytes = 0; long long dd_ne = 0;
     std::vector<Cx<double>> h_tau; std::vector<double> h_S; std::vector<int> h_stop; std::vector<SliceStats> h_stats;
 };
 
@@ -95,6 +96,9 @@ void f64_destroy(F64Runner* R) {
     if (R->tw_cols) cudaFree(R->tw_cols);
     if (R->tw_rows) cudaFree(R->tw_rows);
     if (R->mbits) cudaFree(R->mbits);
+    if (R->dd_keys) cudaFree(R->dd_keys);
+    if (R->dd_vals) cudaFree(R->dd_vals);
+    if (R->dd_temp) cudaFree(R->dd_temp);
     if (R->st) cudaStreamDestroy(R->st);
     delete R;
 }
@@ -234,20 +238,28 @@ int f64_run(F64Runner* R, const p3d_pocs_params* prp, const Cx<float>* x, int x_
                 if (!R->h_stop[i]) {
                     cd tmin, tmax;
                     schedule_bounds(pr, s, ne, tmin, tmax);
-                    x0.resize((size_t)ne);
-                    P3D_CUDA(cudaMemcpy(x0.data(), R->OUT + i * ne, sizeof(Cx<double>) * ne, cudaMemcpyDeviceToHost));
-                    std::vector<cd> cand;
-                    cand.reserve((size_t)ne / 2);
-                    for (const cd& v : x0) if (lex_less(tmin, v) && lex_less(v, tmax)) cand.push_back(v);
-                    P3D_REQUIRE(!cand.empty(), P3D_ERR_NUMERIC, "data-driven schedule: no coefficient between tau_min and tau_max in slice %lld", (long long)(first + i));
-                    std::sort(cand.begin(), cand.end(), [](const cd& a, const cd& b) { return lex_less(b, a); });   // descending
-                    const double nv1 = (double)(cand.size() - 1);
-                    tau[0] = cand[0];
-                    for (int k = 1; k < niter; ++k) {
-                        long long idx = (long long)std::ceil((double)((long long)k * (long long)(cand.size() - 1)) / (double)(niter - 1));
-                        if (idx > (long long)nv1) idx = (long long)nv1;
-                        tau[k] = cand[(size_t)idx];
+                    // order statistics on the device: radix sort of the ordered real parts, ties on the imaginary parts
+                    if (R->dd_ne < ne) {
+                        if (R->dd_keys) cudaFree(R->dd_keys);
+                        if (R->dd_vals) cudaFree(R->dd_vals);
+                        if (R->dd_temp) cudaFree(R->dd_temp);
+                        R->dd_keys = nullptr; R->dd_vals = nullptr; R->dd_temp = nullptr; R->dd_ne = 0;
+                        P3D_CUDA(cudaMalloc(&R->dd_keys, sizeof(unsigned long long) * 2 * ne));
+                        P3D_CUDA(cudaMalloc(&R->dd_vals, sizeof(unsigned int) * 2 * ne));
+                        R->dd_temp_bytes = dd_schedule64_temp_bytes(ne);
+                        P3D_CUDA(cudaMalloc(&R->dd_temp, R->dd_temp_bytes));
+                        R->dd_ne = ne;
                     }
+                    dd_schedule64_device(R->OUT + i * ne, ne, tmin.real(), tmin.imag(), tmax.real(), tmax.imag(), R->stats + i,
+                                         R->tau + i * niter, niter, R->dd_keys, R->dd_vals, R->dd_temp, R->dd_temp_bytes, st);
+                    P3D_CUDA(cudaGetLastError());
+                    std::vector<Cx<double>> ht((size_t)niter);
+                    SliceStats hs;
+                    P3D_CUDA(cudaMemcpyAsync(ht.data(), R->tau + i * niter, sizeof(Cx<double>) * niter, cudaMemcpyDeviceToHost, st));
+                    P3D_CUDA(cudaMemcpyAsync(&hs, R->stats + i, sizeof(SliceStats), cudaMemcpyDeviceToHost, st));
+                    P3D_CUDA(cudaStreamSynchronize(st));
+                    P3D_REQUIRE(hs.n_cand > 0, P3D_ERR_NUMERIC, "data-driven schedule: no coefficient between tau_min and tau_max in slice %lld", (long long)(first + i));
+                    for (int k = 0; k < niter; ++k) tau[k] = cd(ht[k].x, ht[k].y);
                 }
             }
             if (pr.sqrt_decay) apply_sqrt_decay(tau, is_real);

@@ -19,6 +19,13 @@ int f64_run(F64Runner* R, const p3d_pocs_params* pr, const Cx<float>* x, int x_m
             double* tau_out, bool schedule_only, int64_t max_slices);
 
 
+// data-driven schedule from a complex128 X0 on the device (p3d_pocs.cu): tau64[k] = V[ceil(k (Nv - 1) / (niter - 1))] of the
+// candidates strictly between (lo) and (hi) in numpy's complex ordering, sorted descending; keys / vals: 2 * ne entries each
+size_t dd_schedule64_temp_bytes(long long ne);
+void dd_schedule64_device(const Cx<double>* X0, long long ne, double lo_re, double lo_im, double hi_re, double hi_im, SliceStats* stats,
+                          Cx<double>* tau64, int niter, unsigned long long* keys, unsigned int* vals, void* temp, size_t temp_bytes,
+                          cudaStream_t st);
+
 // ---- complex128 kernels for the escalating-precision engine (p3d_pocs.cu): the runner owns tile geometry, tables,
 // register plans and the packed mask of its row kernel; the engine owns the state buffers
 struct F64Kernels {
