@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--niter", type=int, default=0)
     ap.add_argument("--band", type=int, default=-1, help="band_slices override (-1 = plan default)")
     ap.add_argument("--lanes", type=int, default=0, help="copy/compute lanes of the host-buffer path (0 = library default)")
+    ap.add_argument("--chunk", type=int, default=0, help="largest chunk of slices per lane in the host-buffer path (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-diag", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -361,6 +362,8 @@ def main():
 
         if args.lanes > 0:
             plan.set_option("lanes", args.lanes)
+        if args.chunk > 0:
+            plan.set_option("max_slices", args.chunk)
 
         def step_e2e():
             plan.run(hx.array, hm.array, out=ho.array, params=params)
