@@ -76,6 +76,7 @@ struct p3d_plan {
     int64_t pilot_min_elems = 50000; // escalating mode: slices smaller than this run in complex128 from the first iteration (measured:
                                      // 200 x 200 slices gain nothing from the pilot - its launches and the replay cost what it saves -
                                      // 256 x 256 slices gain 13 %)
+    int debug_fail_iter = -1;        // testing: the replay reports a verification failure at this iteration for every slice it replays
     int use_tma = 1;                 // column tiles fetched with cp.async.bulk.tensor where the tile shape allows it
     int watch_mode = -1;             // escalating mode: guard-band hits are verified by the float64 replay instead of freezing the slice
                                      // (-1 = where it pays: slices of 400 k points and more; small slices freeze on the first hit -
@@ -808,7 +809,7 @@ __global__ void __launch_bounds__(128)
 k_replay(const int i, const int* __restrict__ list, const int* __restrict__ kend, int* __restrict__ kfail, const unsigned* __restrict__ arena,
          const int* __restrict__ astart, double2* __restrict__ yval, const int acap, const int niter,
          const Cx<double>* __restrict__ X0, const Cx<double>* __restrict__ mhat, const Cx<double>* __restrict__ tau,
-         const long long first_slice, const int spm, const int n1, const int n2, const double alpha, const double inv_n) {
+         const long long first_slice, const int spm, const int n1, const int n2, const double alpha, const double inv_n, const int debug_fail) {
     __shared__ unsigned sp[128];
     __shared__ double2 sy[128];
     const int s = list[blockIdx.y];
@@ -875,7 +876,7 @@ k_replay(const int i, const int* __restrict__ list, const int* __restrict__ kend
     // the pilot's decision against the exact one: a kept coefficient must survive the float64 threshold, a watched one
     // must not; the first iteration with a mismatch is where complex128 has to take over
     const bool survives = (y.x != 0.0) || (y.y != 0.0);
-    if (survives == watched) atomicMin(&kfail[s], i);
+    if (survives == watched || i == debug_fail) atomicMin(&kfail[s], i);
     if (watched) y = cmake<double>(0.0, 0.0);
     yv[a0 + t] = make_double2(y.x, y.y);
 }
@@ -1216,7 +1217,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
                     const int nb = (int)std::min<int64_t>(band_max, nrl - o);
                     const dim3 grid(gx, (unsigned)nb);
 #define P3D_REPLAY(OPV) k_replay<OPV><<<grid, 128, 0, st>>>(i, L.list + o, L.kend, L.kfail, L.arena, L.astart, L.yval, acap, niter, L.W64, P->mhat, L.tau64, \
-                                                            (long long)first, (int)std::min<int64_t>(R.spm, 0x7fffffff), P->n1, P->n2, pr.alpha, A64.inv_n)
+                                                            (long long)first, (int)std::min<int64_t>(R.spm, 0x7fffffff), P->n1, P->n2, pr.alpha, A64.inv_n, P->debug_fail_iter)
                     if (pr.thresh_op == P3D_OP_HARD) P3D_REPLAY(P3D_OP_HARD);
                     else if (pr.thresh_op == P3D_OP_SOFT) P3D_REPLAY(P3D_OP_SOFT);
                     else P3D_REPLAY(P3D_OP_GARROTE);
@@ -1715,6 +1716,7 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     else if (!strcmp(key, "watch_mode")) P->watch_mode = (int)value;
     else if (!strcmp(key, "use_tma")) P->use_tma = value != 0;
     else if (!strcmp(key, "pilot_min_elems")) P->pilot_min_elems = value;
+    else if (!strcmp(key, "debug_fail_iter")) P->debug_fail_iter = (int)value;
     else if (!strcmp(key, "support_cap")) P->support_cap = (int)std::max<int64_t>(0, value);
     else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(32768, std::max<int64_t>(128, value));
     else if (!strcmp(key, "spec_variant")) {

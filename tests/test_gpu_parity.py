@@ -662,3 +662,48 @@ def test_run_to_run_determinism_all_kernel_families():
     finally:
         sys.argv = argv
     assert glb["only"] == "all" and glb["CASES_RUN"] >= 16
+
+
+# ------------------------------------------------------------------------------------------------
+# escalating mode: the paths that real data rarely take
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,op,watch", [((200, 200), "hard", 1), ((200, 200), "hard", 0), ((256, 256), "garrote", 1),
+                                            ((100, 40), "soft", 0), ((60, 847), "hard", 1)])
+def test_escalating_mode_restart_from_any_verified_iteration(shape, op, watch, p3d):
+    """The replay verifies the pilot's decisions; a failed verification at iteration i restarts complex128 from the last
+    verified iterate.  Forced here at iterations 0, 3 and 9 for every slice (plan option `debug_fail_iter`), with the
+    watch list on and off, register and generic kernels, an all-zero slice and an early-exit run in the batch: the
+    result must still be the float64 mode's (a restart from ANY verified iteration is exact)."""
+    x, mask = make_input(dict(seed=21, shape=shape, keep=0.3, nwaves=5, noise=0.01))
+    x = np.stack([x, 0.5 * np.conj(x), np.zeros_like(x), 2.0 * x[::-1, ::-1] * mask]).astype(np.complex64)
+    for eps in (0.0, 1e-7):
+        params = dict(niter=24, thresh_op=op, thresh_model="exponential", eps=eps, alpha=1.0, p_max=0.99, p_min=1e-5)
+        ref, iref = p3d.PocsPlan(*shape, precision=64).run(x, mask, **params)
+        for fail_at in (-1, 0, 3, 9):
+            plan = p3d.PocsPlan(*shape)
+            plan.set_option("pilot_min_elems", 0)
+            plan.set_option("watch_mode", watch)
+            plan.set_option("debug_fail_iter", fail_at)
+            y, info = plan.run(x, mask, **params)
+            assert list(info["niterations"]) == list(iref["niterations"]), (fail_at, eps)
+            assert rel_l2(y, ref) <= 2e-7, (fail_at, eps, rel_l2(y, ref))
+            assert np.array_equal(y[2], x[2]) and info["niterations"][2] == 0
+            plan.close()
+
+
+def test_escalating_mode_many_slices_in_one_call(p3d):
+    """more slices than one launch takes (band_max = 32768): the compacted lists are split across launches."""
+    x, mask = make_input(dict(seed=4, shape=(8, 12), keep=0.5, nwaves=2))
+    n = 33000
+    scale = (1.0 + (np.arange(n) % 17) / 16.0).astype(np.float32)
+    xs = (x.astype(np.complex64)[None] * scale[:, None, None]).astype(np.complex64)
+    params = dict(niter=6, thresh_op="hard", thresh_model="exponential", eps=0.0, alpha=1.0, p_max=0.99, p_min=1e-3)
+    plan = p3d.PocsPlan(8, 12)
+    plan.set_option("pilot_min_elems", 0)
+    y, info = plan.run(xs, mask, **params)
+    assert np.all(info["niterations"] == 6)
+    for i in (0, 5, 16, 32767, 32768, 32999):
+        ref = orc.pocs_slice(xs[i].astype(np.complex128), mask, **params)
+        assert rel_l2(y[i], ref) <= RTOL, (i, rel_l2(y[i], ref))
+    # slices that differ by a power-of-two factor are bit-identical up to that factor
+    assert np.array_equal(y[16], 2 * y[0])
