@@ -33,7 +33,7 @@ __device__ __forceinline__ void mix_twiddle(Cx<T> (&x)[R], const Cx<T>* __restri
     } else if constexpr (sizeof(T) == 8 && (R > 3)) {
         // complex128: powers of W^k instead of R - 1 table loads (see twiddle_powers)
         Cx<double> w[R];
-        twiddle_powers<R>(tab[tw_index(R, Ns, 1, 0) + k * (R % 2 == 0 ? 2 : 1)], w);
+        twiddle_powers<R, double>(tab[tw_index(R, Ns, 1, 0) + k * (R % 2 == 0 ? 2 : 1)], w);
 #pragma unroll
         for (int r = 1; r < R; ++r) x[r] = (DIR < 0) ? cmul(x[r], w[r]) : cmulc(x[r], w[r]);
     } else {

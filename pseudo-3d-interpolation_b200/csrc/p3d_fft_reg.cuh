@@ -67,13 +67,13 @@ __host__ __device__ constexpr int tw_index(int R, int Ns, int r, int k) {
 // complex128 twiddles: W^{r k}, r = 2 .. R-1, from W^k alone (squares and products, depth <= 4).  The L1 / shared-memory
 // data pipe is the busiest unit of the complex128 kernels (ncu: 80 % in the row kernel) and R - 1 16-byte table loads per
 // butterfly were a quarter of its wavefronts; the FP64 pipe has the headroom for the 3 - 4 extra instructions per factor.
-template <int R>
-__device__ __forceinline__ void twiddle_powers(const Cx<double> w1, Cx<double> (&w)[R]) {
-    w[0] = cmake<double>(1.0, 0.0);
+template <int R, typename T>
+__device__ __forceinline__ void twiddle_powers(const Cx<T> w1, Cx<T> (&w)[R]) {
+    w[0] = cmake<T>(T(1), T(0));
     w[1] = w1;
 #pragma unroll
     for (int r = 2; r < R; ++r) {
-        if (r % 2 == 0) { const Cx<double> h = w[r / 2]; w[r] = cmake<double>(h.x * h.x - h.y * h.y, 2.0 * h.x * h.y); }
+        if (r % 2 == 0) { const Cx<T> h = w[r / 2]; w[r] = cmake<T>(h.x * h.x - h.y * h.y, T(2) * h.x * h.y); }
         else w[r] = cmul(w[(r + 1) / 2], w[r / 2]);
     }
 }
@@ -126,7 +126,7 @@ struct RegPasses<N, E, DIR, Ns, BUF, TWOFF, T, Acc, R, Rest...> {
                 } else if constexpr (sizeof(T) == 8 && (R > 3)) {
                     const Cx<T>* tp = tw + TWOFF;
                     Cx<double> w[R];
-                    twiddle_powers<R>(tp[tw_index(R, Ns, 1, 0) + k * (R % 2 == 0 ? 2 : 1)], w);
+                    twiddle_powers<R, double>(tp[tw_index(R, Ns, 1, 0) + k * (R % 2 == 0 ? 2 : 1)], w);
 #pragma unroll
                     for (int r = 1; r < R; ++r) x[r] = (DIR < 0) ? cmul(x[r], w[r]) : cmulc(x[r], w[r]);
                 } else {
