@@ -529,7 +529,13 @@ def pocs_cube(cube, fold_or_mask, devices=None, out=None, results=None, precisio
             if hi <= lo:
                 return
             plan = get_plan(n1, n2, dev, precision)
-            _, info = plan.run(xin[lo:hi], mask, out=res[lo:hi], params=params)
+            try:
+                _, info = plan.run(xin[lo:hi], mask, out=res[lo:hi], params=params)
+            except MemoryError:
+                # cached plans of other shapes keep their lane buffers (sized for their largest call): drop them and retry
+                release_plans()
+                plan = get_plan(n1, n2, dev, precision)
+                _, info = plan.run(xin[lo:hi], mask, out=res[lo:hi], params=params)
             nit[lo:hi] = info["niterations"]
             cost[lo:hi] = info["cost"]
         except Exception as e:      # noqa: BLE001 - re-raised below
