@@ -164,12 +164,20 @@ int p3d_plan_event_elapsed_ms(p3d_plan* plan, int slot_a, int slot_b, double* ms
 /* Human-readable description of the chosen kernels / tiles / bands (for DESIGN.md and bench). */
 int p3d_plan_describe(p3d_plan* plan, char* buf, int64_t buflen);
 /* Options: key in {"band_slices","force_generic","lanes","max_slices","spec_variant","spec_variant64",
- *   "precision"    0 (default) = escalating: a slice iterates in fp32 until a coefficient of its spectrum comes within the
- *                  guard band of the threshold, and in complex128 from that iterate on (meets the 1e-4 of the float64
- *                  reference at about 60 % of the fp32 rate); 32 = fp32 only (fastest; hard-threshold decisions may
- *                  differ from float64 once tau_k reaches the dense part of the spectrum); 64 = complex128 throughout,
+ *   "precision"    0 (default) = escalating: an fp32 pilot decides the thresholds while the spectrum is sparse and records the
+ *                  surviving coefficients, the float64 trajectory is rebuilt exactly from that record (sparse-domain
+ *                  replay) and the remaining iterations run on complex128 state (meets the 1e-4 of the float64 reference -
+ *                  in fact reproduces the float64 mode - at about 60 % of the fp32 rate); 32 = fp32 only (fastest;
+ *                  threshold decisions may differ from float64 once tau_k reaches the dense part of the spectrum: 1e-3);
+ *                  64 = complex128 throughout,
  *   "guard_factor" half-width of the guard band in units of 2^-24 * rms|X| (default 1024; 0 disables the switch),
- *   "seg_iters"    iterations between two compactions of the fp32 slice list (default 4)} */
+ *   "watch_mode"   -1 (default) / 0 / 1: guard-band hits are recorded and verified exactly by the float64 replay instead
+ *                  of freezing the slice (-1: for slices of 400 k points and more),
+ *   "arena_cap"    support-record entries per slice (default 16384), "support_cap" largest support replayed per
+ *                  iteration (0 = 2.2 sqrt(n_iline n_xline)), "pilot_min_elems" slices smaller than this skip the fp32
+ *                  pilot (default 50000), "seg_iters" iterations between two compactions of the fp32 slice list (4),
+ *   "use_tma"      1 (default) / 0: column tiles fetched with cp.async.bulk.tensor where the tile shape allows it,
+ *   "debug_fail_iter" testing only: the replay reports a failed verification at this iteration (-1 = off)} */
 int p3d_plan_set_option(p3d_plan* plan, const char* key, int64_t value);
 /* Escalating mode, last p3d_pocs_run of this plan: slices that switched to complex128 and the slice-iterations they
  * ran there (either pointer may be NULL). */

@@ -1017,7 +1017,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
         B.adaptive = 0; B.accum = 1; B.store_x0 = 0;
         for_list32(B, L.list, (int)count, [&](const BandArgs<float>& b, int nb) { launch_rows_init(P, L, b, nb); });
         BandArgs<double> B64 = A64;
-        B64.adaptive = 0; B64.accum = 0; B64.src_out = 0; B64.store_x0_inplace = 1;
+        B64.adaptive = 0; B64.accum = 0; B64.store_x0_inplace = 1;
         rows_init64(B64, L.list, (int)count);
         prof_begin(P, L.events, st, 10);
         for (int64_t o = 0; o < count; o += band_max) {
@@ -1268,7 +1268,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             const int* list1 = L.list + n0;
             if (n0 > 0) {
                 BandArgs<double> B64 = A64;
-                B64.src_out = 0; B64.adaptive = adaptive ? 1 : 0; B64.accum = 0;
+                B64.adaptive = adaptive ? 1 : 0; B64.accum = 0;
                 rows_init64(B64, L.list, n0);
             }
             if (n1r > 0) {

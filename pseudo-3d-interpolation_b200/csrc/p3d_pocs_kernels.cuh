@@ -97,7 +97,6 @@ template <typename T> struct BandArgs {
     const float* guard;          // optional [band]: half-width of that guard band (fp32 kernels only)
     const Cx<float>* D32;        // complex128 kernels with complex64 observed data / results (no converted copies)
     Cx<float>* OUT32;
-    int src_out;                 // init kernels: source is OUT32 (the fp32 iterate handed over) instead of D32
     double2* cand;               // complex128 statistics: per-CTA lexicographic maxima [band][cand_stride]
     int cand_stride;
     // support record of the fp32 pilot (exact restart): packed (row << 16 | col) of every coefficient kept in iteration k
@@ -502,19 +501,8 @@ __global__ void __launch_bounds__(512) k_rows_generic(const __grid_constant__ Po
             const int rr = w / G.n2, j = w - rr * G.n2;
             const long long g = row_off + (long long)rr * G.n2 + j;
             Cx<T> d;
-            if (A.D32) { const Cx<float> t = A.src_out ? A.OUT32[g] : A.D32[g]; d = cmake<T>((T)t.x, (T)t.y); }
+            if (A.D32) { const Cx<float> t = A.D32[g]; d = cmake<T>((T)t.x, (T)t.y); }
             else d = A.D[g];
-            if (A.src_out) {
-                // hand-over of an fp32 iterate x_k: plain row FFT, or the APOCS step with x_old = x_k (functions/POCS.py:572-575)
-                if (A.adaptive) {
-                    const Cx<float> t = A.D32[g];
-                    const Cx<T> dd = cmake<T>((T)t.x, (T)t.y);
-                    const T m = (T)A.mask[mask_off + (long long)rr * G.n2 + j];
-                    const T keep = T(1) - A.alpha * m, om = T(1) - A.alpha;
-                    const Cx<T> xt = cmake<T>(A.alpha * dd.x + keep * d.x, A.alpha * dd.y + keep * d.y);
-                    d = cmake<T>(xt.x + om * (dd.x - m * d.x), xt.y + om * (dd.y - m * d.y));
-                }
-            } else
             if (!A.adaptive) {
                 nnz += (d.x != T(0) || d.y != T(0)) ? 1ull : 0ull;
                 part += (double)sqrt(d.x * d.x + d.y * d.y);

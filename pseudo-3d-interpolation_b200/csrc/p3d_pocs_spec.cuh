@@ -53,7 +53,7 @@ struct SpecKernels64 {
     RowsIterLaunch64 rows_iter = nullptr;
     // escalating-precision mode: complex128 state beside complex64 observed data / results (BandArgs::D32 / OUT32)
     RowsIterLaunch64 rows_iter_io32 = nullptr;
-    RowsIterLaunch64 rows_init_io32 = nullptr;   // row FFT of a complex64 slice (observed data, or the fp32 iterate handed over)
+    RowsIterLaunch64 rows_init_io32 = nullptr;   // row FFT (complex128) of the complex64 observed slice
     RowsIterLaunch64 cols_stats = nullptr;       // column FFT + exact statistics (per-CTA lexicographic maxima in BandArgs::cand)
     int cols_C = 0;                               // columns per tile of cols_stats (cand entries per slice = ceil(n2 / cols_C))
     PackMaskLaunch pack_mask = nullptr;

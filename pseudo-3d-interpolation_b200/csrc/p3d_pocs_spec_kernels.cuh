@@ -300,8 +300,7 @@ k_rows_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, co
 }
 
 // ---- once-per-slice kernels: row FFT of the observed slice, column FFT + schedule statistics -------
-// F = float: the observed slice A.D.  F = double (IO32): complex64 source = the observed slice A.D32 or, with
-// A.src_out, the fp32 iterate x_k that the escalating mode hands over in A.OUT32.
+// F = float: the observed slice A.D.  F = double (IO32): the complex64 observed slice A.D32.
 template <typename F, typename LP, int RB, int MINB>
 __global__ void __launch_bounds__(LP::T* RB, MINB)
 k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ tw, const __grid_constant__ BandArgs<F> A) {
@@ -321,14 +320,8 @@ k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ t
     const Cx<float>* __restrict__ Dp = (IO32 ? A.D32 : reinterpret_cast<const Cx<float>*>(A.D)) + off;
     Cx<F>* __restrict__ Wp = A.W + off;
     Cx<F> v[E];
-    if (IO32 && A.src_out) {
-        const Cx<float>* __restrict__ Xp = A.OUT32 + off;
 #pragma unroll
-        for (int e = 0; e < E; ++e) { const Cx<float> t = ok ? Xp[e * T] : cmake<float>(0.f, 0.f); v[e] = cmake<F>((F)t.x, (F)t.y); }
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) { const Cx<float> t = ok ? Dp[e * T] : cmake<float>(0.f, 0.f); v[e] = cmake<F>((F)t.x, (F)t.y); }
-    }
+    for (int e = 0; e < E; ++e) { const Cx<float> t = ok ? Dp[e * T] : cmake<float>(0.f, 0.f); v[e] = cmake<F>((F)t.x, (F)t.y); }
     F part = F(0);
     unsigned long long nnz = 0ull;
     if (!A.adaptive) {
@@ -338,18 +331,16 @@ k_rows_init_spec(const __grid_constant__ PocsGeom G, const Cx<F>* __restrict__ t
             part += sqrt(v[e].x * v[e].x + v[e].y * v[e].y);
         }
     } else {
-        // APOCS prologue (functions/POCS.py:572-575) with x_old = x, or x_old = the iterate handed over
+        // APOCS prologue with x_old = x (functions/POCS.py:572-575)
         const long long midx = (A.first_slice + s) / G.slices_per_mask;
         const unsigned mbits = ok ? A.mbits[(midx * G.n1 + row) * T + j] : 0u;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const F m = ((mbits >> e) & 1u) ? F(1) : F(0);
             const F keep = F(1) - A.alpha * m, om = F(1) - A.alpha;
-            const Cx<F> xo = v[e];
-            Cx<F> d = xo;
-            if (IO32 && A.src_out) { const Cx<float> t = ok ? Dp[e * T] : cmake<float>(0.f, 0.f); d = cmake<F>((F)t.x, (F)t.y); }
-            const Cx<F> xt = cmake<F>(A.alpha * d.x + keep * xo.x, A.alpha * d.y + keep * xo.y);
-            v[e] = cmake<F>(xt.x + om * (d.x - m * xo.x), xt.y + om * (d.y - m * xo.y));
+            const Cx<F> d = v[e];
+            const Cx<F> xt = cmake<F>(A.alpha * d.x + keep * d.x, A.alpha * d.y + keep * d.y);
+            v[e] = cmake<F>(xt.x + om * (d.x - m * d.x), xt.y + om * (d.y - m * d.y));
         }
     }
     if (A.accum) {
