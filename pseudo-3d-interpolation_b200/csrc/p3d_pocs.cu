@@ -71,6 +71,9 @@ struct p3d_plan {
     int precision = 0;               // 0: escalating (fp32 state, complex128 once a coefficient enters the guard band of the
                                      // threshold), 32: fp32 only, 64: float64 state mode (p3d_pocs_f64.cu)
     double guard_factor = 1024.0;    // guard half-width in units of eps32 * rms|X| (escalating mode)
+    double watch_guard_factor = 4096.0;   // the same where a hit is only recorded and verified (watch list): a wider band costs
+                                          // a few more replayed entries, not an earlier switch (fp32 deviation of coefficients
+                                          // near the threshold measured on config 2: up to 260 units late in the pilot)
     int seg_iters = 4;               // escalating mode: iterations between two compactions of the active-slice list
     int arena_cap = 16384;           // escalating mode: support-record entries per slice (all pilot iterations together)
     int64_t pilot_min_elems = 50000; // escalating mode: slices smaller than this run in complex128 from the first iteration (measured:
@@ -1037,7 +1040,12 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
     std::vector<cd> tau;
     const double eps32 = 5.9604644775390625e-08;      // 2^-24
     // adaptive POCS has no sparse recursion of this form: complex128 from the first iteration (an infinite guard band)
-    const double gfac = (adaptive || ne < P->pilot_min_elems) ? std::numeric_limits<double>::infinity() : P->guard_factor;
+    // watch list (kernels that record the guard band; bit 31 of an entry must be free): a hit is verified by the replay
+    // instead of freezing the slice
+    const bool want_watch = P->watch_mode < 0 ? (ne >= 400000) : (P->watch_mode != 0);
+    const bool watch = want_watch && P->spec.cols_iter && !P->force_generic && P->n1 < 32768 && !adaptive;
+    const double gfac = (adaptive || ne < P->pilot_min_elems) ? std::numeric_limits<double>::infinity()
+                                                               : (watch ? std::max(P->guard_factor, P->watch_guard_factor) : P->guard_factor);
     auto store_tau = [&](int64_t i) {
         for (int k = 0; k < niter; ++k) {
             L.h_tau[i * niter + k] = cmake<float>((float)tau[k].real(), (float)tau[k].imag());
@@ -1148,10 +1156,7 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             if (guard_on) {
                 B.arena = L.arena; B.acnt = L.acnt; B.astart = L.astart; B.arena_cap = acap;
                 B.scap = P->support_cap > 0 ? P->support_cap : (int)(2.2 * std::sqrt((double)ne));
-                // watch list (kernels that record the guard band; bit 31 of an entry must be free): a hit is verified by
-                // the replay instead of freezing the slice
-                const bool want_watch = P->watch_mode < 0 ? (ne >= 400000) : (P->watch_mode != 0);
-                B.watch = (want_watch && P->spec.cols_iter && !P->force_generic && P->n1 < 32768 && !adaptive) ? 1 : 0;
+                B.watch = watch ? 1 : 0;
                 B.wflag = L.wflag;
             }
             B.k = k; B.last = (k == niter - 1) ? 1 : 0;
@@ -1711,7 +1716,8 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
         if (value != 0 && value != 32 && value != 64) { set_error("precision must be 0 (escalating), 32 or 64"); return P3D_ERR_BAD_ARG; }
         P->precision = (int)value;
     }
-    else if (!strcmp(key, "guard_factor")) P->guard_factor = (double)value;
+    else if (!strcmp(key, "guard_factor")) { P->guard_factor = (double)value; if (value == 0) P->watch_guard_factor = 0.0; }
+    else if (!strcmp(key, "watch_guard_factor")) P->watch_guard_factor = (double)value;
     else if (!strcmp(key, "seg_iters")) P->seg_iters = (int)std::max<int64_t>(1, value);
     else if (!strcmp(key, "watch_mode")) P->watch_mode = (int)value;
     else if (!strcmp(key, "use_tma")) P->use_tma = value != 0;
