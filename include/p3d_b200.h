@@ -175,7 +175,7 @@ int p3d_plan_describe(p3d_plan* plan, char* buf, int64_t buflen);
  *                  of freezing the slice (-1: for slices of 400 k points and more),
  *   "arena_cap"    support-record entries per slice (default 16384), "support_cap" largest support replayed per
  *                  iteration (0 = 2.2 sqrt(n_iline n_xline)), "pilot_min_elems" slices smaller than this skip the fp32
- *                  pilot (default 50000), "seg_iters" iterations between two compactions of the fp32 slice list (4),
+ *                  pilot (default 0), "fused_replay_max" largest support replayed by the one-launch kernel (1024), "seg_iters" iterations between two compactions of the fp32 slice list (4),
  *   "use_tma"      1 (default) / 0: column tiles fetched with cp.async.bulk.tensor where the tile shape allows it,
  *   "debug_fail_iter" testing only: the replay reports a failed verification at this iteration (-1 = off)} */
 int p3d_plan_set_option(p3d_plan* plan, const char* key, int64_t value);

@@ -76,9 +76,9 @@ struct p3d_plan {
                                           // near the threshold measured on config 2: up to 260 units late in the pilot)
     int seg_iters = 4;               // escalating mode: iterations between two compactions of the active-slice list
     int arena_cap = 16384;           // escalating mode: support-record entries per slice (all pilot iterations together)
-    int64_t pilot_min_elems = 50000; // escalating mode: slices smaller than this run in complex128 from the first iteration (measured:
-                                     // 200 x 200 slices gain nothing from the pilot - its launches and the replay cost what it saves -
-                                     // 256 x 256 slices gain 13 %)
+    int64_t pilot_min_elems = 0;     // escalating mode: slices smaller than this run in complex128 from the first iteration (0: every
+                                     // size has a pilot; with the one-launch replay it pays even for 200 x 200 slices: +3.5 %)
+    int fused_replay_max = 1024;     // largest per-iteration support (rounded up to a power of two) replayed by the one-launch kernel
     int debug_fail_iter = -1;        // testing: the replay reports a verification failure at this iteration for every slice it replays
     int use_tma = 1;                 // column tiles fetched with cp.async.bulk.tensor where the tile shape allows it
     int watch_mode = -1;             // escalating mode: guard-band hits are verified by the float64 replay instead of freezing the slice
@@ -884,6 +884,102 @@ k_replay(const int i, const int* __restrict__ list, const int* __restrict__ kend
     yv[a0 + t] = make_double2(y.x, y.y);
 }
 
+
+// The whole replay of a slice in ONE launch (small supports: launch-bound otherwise): one CTA per slice walks through the
+// pilot's iterations, keeps the previous support and its values in shared memory, sorts each iteration's record
+// (fixed summation order) and verifies the pilot's decisions like k_replay.  Dynamic shared memory: 2 x maxseg x 20 bytes.
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_replay_fused(const int* __restrict__ list, const int* __restrict__ kend, int* __restrict__ kfail, unsigned* __restrict__ arena,
+               const int* __restrict__ astart, double2* __restrict__ yval, const int acap, const int niter, const int maxseg,
+               const Cx<double>* __restrict__ X0, const Cx<double>* __restrict__ mhat, const Cx<double>* __restrict__ tau,
+               const long long first_slice, const int spm, const int n1, const int n2, const double alpha, const double inv_n,
+               const int debug_fail) {
+    extern __shared__ __align__(16) unsigned char fused_sh[];
+    double2* ybuf = reinterpret_cast<double2*>(fused_sh);                          // [2][maxseg]
+    unsigned* ibuf = reinterpret_cast<unsigned*>(fused_sh + (size_t)2 * maxseg * sizeof(double2));   // [2][maxseg]
+    const int s = list[blockIdx.x];
+    const int ke = kend[s];
+    const int* as = astart + (long long)s * (niter + 1);
+    unsigned* ar = arena + (long long)s * acap;
+    double2* yv = yval + (long long)s * acap;
+    const long long ne = (long long)n1 * n2;
+    const Cx<double>* __restrict__ x0s = X0 + (long long)s * ne;
+    const double2* __restrict__ mh = reinterpret_cast<const double2*>(mhat + ((first_slice + s) / spm) * ne);
+    int cur = 0, np = 0;
+    for (int i = 0; i < ke; ++i) {
+        const int a0 = as[i], n = as[i + 1] - a0;
+        unsigned* ic = ibuf + (size_t)cur * maxseg;
+        double2* yc = ybuf + (size_t)cur * maxseg;
+        const unsigned* ip = ibuf + (size_t)(cur ^ 1) * maxseg;
+        const double2* yp = ybuf + (size_t)(cur ^ 1) * maxseg;
+        // this iteration's record, sorted ascending
+        int m = 1; while (m < n) m <<= 1;
+        for (int t = threadIdx.x; t < m; t += blockDim.x) ic[t] = t < n ? ar[a0 + t] : 0xffffffffu;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < m; t += blockDim.x) {
+                    const int p = t ^ j;
+                    if (p > t) {
+                        const unsigned a = ic[t], b = ic[p];
+                        if ((a > b) == ((t & k) == 0)) { ic[t] = b; ic[p] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const unsigned ent = ic[t];
+            ar[a0 + t] = ent;                                   // the restart scatters from the sorted record
+            const bool watched = (ent >> 31) != 0u;
+            const unsigned pj = ent & 0x7fffffffu;
+            const int jr = (int)(pj >> 16), jc = (int)(pj & 0xffffu);
+            const Cx<double> x0 = x0s[(long long)jr * n2 + jc];
+            double accx = 0.0, accy = 0.0, selfx = 0.0, selfy = 0.0;
+            int q = 0;
+            for (; q + 8 <= np; q += 8) {
+                double2 mm[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned ps = ip[q + u] & 0x7fffffffu;
+                    int dr = jr - (int)(ps >> 16); if (dr < 0) dr += n1;
+                    int dc = jc - (int)(ps & 0xffffu); if (dc < 0) dc += n2;
+                    mm[u] = __ldg(mh + (long long)dr * n2 + dc);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double2 ys = yp[q + u];
+                    if ((ip[q + u] & 0x7fffffffu) == pj) { selfx = ys.x; selfy = ys.y; }
+                    accx += mm[u].x * ys.x - mm[u].y * ys.y;
+                    accy += mm[u].x * ys.y + mm[u].y * ys.x;
+                }
+            }
+            for (; q < np; ++q) {
+                const unsigned ps = ip[q] & 0x7fffffffu;
+                const double2 ys = yp[q];
+                if (ps == pj) { selfx = ys.x; selfy = ys.y; }
+                int dr = jr - (int)(ps >> 16); if (dr < 0) dr += n1;
+                int dc = jc - (int)(ps & 0xffffu); if (dc < 0) dc += n2;
+                const double2 mv = __ldg(mh + (long long)dr * n2 + dc);
+                accx += mv.x * ys.x - mv.y * ys.y;
+                accy += mv.x * ys.y + mv.y * ys.x;
+            }
+            Cx<double> X = x0;
+            if (i > 0) X = cmake<double>(alpha * x0.x + selfx - alpha * inv_n * accx, alpha * x0.y + selfy - alpha * inv_n * accy);
+            const Cx<double> tk = tau[(long long)s * niter + i];
+            const double a = tk.x, b = tk.y;
+            Cx<double> y = apply_threshold<OP, double>(X, a, b, a * a - b * b, 2.0 * a * b);
+            const bool survives = (y.x != 0.0) || (y.y != 0.0);
+            if (survives == watched || i == debug_fail) atomicMin(&kfail[s], i);
+            if (watched) y = cmake<double>(0.0, 0.0);
+            yc[t] = make_double2(y.x, y.y);
+            yv[a0 + t] = make_double2(y.x, y.y);
+        }
+        __syncthreads();
+        np = n; cur ^= 1;
+    }
+}
+
 // restart spectrum of a frozen slice: zero, then y_{k_e - 1} at its support
 __global__ void k_zero_slices(const int* __restrict__ list, Cx<double>* W, long long ne) {
     const int s = list[blockIdx.y];
@@ -1209,6 +1305,24 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
             P3D_CUDA(cudaMemcpyAsync(L.kend, L.h_kend, sizeof(int) * count, cudaMemcpyHostToDevice, st));
             const int nrl = (int)rl.size();
             int pow2 = 1; while (pow2 < seg_max) pow2 <<= 1;
+            const int spm_i = (int)std::min<int64_t>(R.spm, 0x7fffffff);
+            if (pow2 <= P->fused_replay_max) {
+                // small supports: the whole replay of a slice in one launch (one CTA per slice)
+                const size_t smem = (size_t)2 * pow2 * (sizeof(double2) + sizeof(unsigned));
+                static bool fused_cfg = false;
+                if (!fused_cfg) {
+                    cudaFuncSetAttribute(k_replay_fused<P3D_OP_HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 20);
+                    cudaFuncSetAttribute(k_replay_fused<P3D_OP_SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 20);
+                    cudaFuncSetAttribute(k_replay_fused<P3D_OP_GARROTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 20);
+                    fused_cfg = true;
+                }
+#define P3D_REPLAY_F(OPV) k_replay_fused<OPV><<<(unsigned)nrl, 256, smem, st>>>(L.list, L.kend, L.kfail, L.arena, L.astart, L.yval, acap, niter, pow2, L.W64, P->mhat, \
+                                                                               L.tau64, (long long)first, spm_i, P->n1, P->n2, pr.alpha, A64.inv_n, P->debug_fail_iter)
+                if (pr.thresh_op == P3D_OP_HARD) P3D_REPLAY_F(P3D_OP_HARD);
+                else if (pr.thresh_op == P3D_OP_SOFT) P3D_REPLAY_F(P3D_OP_SOFT);
+                else P3D_REPLAY_F(P3D_OP_GARROTE);
+#undef P3D_REPLAY_F
+            } else {
             static bool sort_cfg = false;
             if (!sort_cfg) { cudaFuncSetAttribute(k_sort_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4); sort_cfg = true; }
             for (int64_t o = 0; o < nrl; o += band_max) {
@@ -1222,12 +1336,13 @@ void process_chunk_esc(RunCtx& R, Lane& L, int64_t first, int64_t count) {
                     const int nb = (int)std::min<int64_t>(band_max, nrl - o);
                     const dim3 grid(gx, (unsigned)nb);
 #define P3D_REPLAY(OPV) k_replay<OPV><<<grid, 128, 0, st>>>(i, L.list + o, L.kend, L.kfail, L.arena, L.astart, L.yval, acap, niter, L.W64, P->mhat, L.tau64, \
-                                                            (long long)first, (int)std::min<int64_t>(R.spm, 0x7fffffff), P->n1, P->n2, pr.alpha, A64.inv_n, P->debug_fail_iter)
+                                                            (long long)first, spm_i, P->n1, P->n2, pr.alpha, A64.inv_n, P->debug_fail_iter)
                     if (pr.thresh_op == P3D_OP_HARD) P3D_REPLAY(P3D_OP_HARD);
                     else if (pr.thresh_op == P3D_OP_SOFT) P3D_REPLAY(P3D_OP_SOFT);
                     else P3D_REPLAY(P3D_OP_GARROTE);
 #undef P3D_REPLAY
                 }
+            }
             }
             prof_end(P, L.events, st);
             P3D_CUDA(cudaGetLastError());
@@ -1723,6 +1838,7 @@ int p3d_plan_set_option(p3d_plan* P, const char* key, int64_t value) {
     else if (!strcmp(key, "use_tma")) P->use_tma = value != 0;
     else if (!strcmp(key, "pilot_min_elems")) P->pilot_min_elems = value;
     else if (!strcmp(key, "debug_fail_iter")) P->debug_fail_iter = (int)value;
+    else if (!strcmp(key, "fused_replay_max")) P->fused_replay_max = (int)std::min<int64_t>(4096, std::max<int64_t>(0, value));
     else if (!strcmp(key, "support_cap")) P->support_cap = (int)std::max<int64_t>(0, value);
     else if (!strcmp(key, "arena_cap")) P->arena_cap = (int)std::min<int64_t>(32768, std::max<int64_t>(128, value));
     else if (!strcmp(key, "spec_variant")) {
