@@ -140,6 +140,11 @@ int p3d_time_envelope(int device, const float* x, int x_mem, float* out, int out
 /* Device time (CUDA events) spent in the kernels of this thread's last p3d_time_fft / p3d_time_ifft
  * call (0 when the call used the generic direct kernels). */
 int p3d_time_last_kernel_ms(double* ms);
+/* Which kernels served this thread's last p3d_time_* call: "tma" (one pass: TMA-staged tiles, register FFT; record
+ * lengths 512 / 1000 / 1024 / 2000 / 2048 / 2500 / 4000 / 4096 with a trace count divisible by 4), "pipeline"
+ * (transpose / FFT / transpose through L2), "direct" or "generic" (any length).  Environment: P3D_TIME_PATH =
+ * tma | pipeline | direct selects the first candidate (read at every call). */
+const char* p3d_time_last_path(void);
 
 /* Pinned host memory for asynchronous copies. */
 int p3d_host_alloc(void** ptr, int64_t bytes);

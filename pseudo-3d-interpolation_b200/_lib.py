@@ -56,6 +56,7 @@ SIGNATURES = {
                                 C.c_double, C.c_double, C.c_int, C.c_int]),
     "p3d_time_envelope": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int64]),
     "p3d_time_last_kernel_ms": (C.c_int, [C.POINTER(C.c_double)]),
+    "p3d_time_last_path": (C.c_char_p, []),
     "p3d_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "p3d_host_free": (C.c_int, [C.c_void_p]),
     "p3d_device_alloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64]),

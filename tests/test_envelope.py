@@ -56,3 +56,19 @@ def test_gpu_envelope_lengths_and_axes(nt, ntr):
         z = x.reshape(nt, ntr, 1).astype(np.float64)
         ez = timeaxis.envelope(z, axis=0)
         assert ez.dtype == np.float64 and ez.shape == z.shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["tma", "pipeline"])
+@pytest.mark.parametrize("nt,ntr", [(512, 740), (1024, 260), (2048, 108), (4096, 44), (1000, 332), (2000, 100), (2500, 52), (4000, 36)])
+def test_gpu_envelope_one_pass_and_pipeline(nt, ntr, path, monkeypatch):
+    """the one-pass TMA-staged envelope kernel (trace counts divisible by 4; three CTAs, so every CTA walks over several tiles,
+    the last one partial) and the transposing pipeline on the same input"""
+    from pseudo_3d_interpolation_b200 import timeaxis, _lib
+    monkeypatch.setenv("P3D_TIME_PATH", path)
+    monkeypatch.setenv("P3D_TIME_GRID", "3")
+    rng = np.random.default_rng(nt + ntr)
+    x = rng.standard_normal((nt, ntr)).astype(np.float32)
+    e = timeaxis.envelope(x, axis=0)
+    assert _lib.load().p3d_time_last_path().decode() == path
+    np.testing.assert_allclose(e, orc.envelope(x, axis=0), rtol=0, atol=2e-5 * np.sqrt(np.log2(nt)))

@@ -577,6 +577,48 @@ def test_time_axis_register_pipeline_sizes(nt, shape, real, up, p3d):
         assert rel_l2(xb, xr[:nte]) < 5e-6
 
 
+@pytest.mark.parametrize("path", ["tma", "pipeline", "direct"])
+@pytest.mark.parametrize("nt,shape,real,up", [(2048, (12, 11), True, 1), (2048, (4, 9), False, 1), (1024, (8, 25), True, 1), (512, (16, 23), False, 1),
+                                              (256, (32, 7), True, 2), (4096, (4, 5), True, 1), (4096, (2, 6), False, 1),
+                                              (1000, (8, 21), True, 1), (1000, (4, 17), False, 1), (2000, (4, 13), True, 1), (2500, (4, 9), True, 1),
+                                              (4000, (4, 7), True, 1), (500, (4, 5), True, 2), (1024, (4, 3), False, 2)])
+def test_time_axis_paths(nt, shape, real, up, path, p3d, monkeypatch):
+    """The three implementations of the time-axis transforms (one pass with TMA-staged tiles - the default -, the
+    transposing pipeline, the direct register kernels) against the numpy oracle, on trace counts divisible by 4 (what the
+    one-pass kernels need) with a partial last tile, and with so few CTAs that every CTA walks over several tiles
+    (both shared-memory stages, both mbarrier phases).  up = 2: zero padding to the plan length."""
+    from oracle import time_axis_oracle as tor
+    from pseudo_3d_interpolation_b200 import timeaxis, synth, _lib
+    monkeypatch.setenv("P3D_TIME_PATH", path)
+    monkeypatch.setenv("P3D_TIME_GRID", "3")
+    rng = np.random.default_rng(nt + shape[1])
+    x = rng.standard_normal((nt,) + shape).astype(np.float32)
+    twt = synth.T0_MS + synth.DT_MS * np.arange(nt)
+    kw = dict(upsampling_factor=up)
+    F, f = timeaxis.time_fft(x, twt, compute_real=real, **kw)
+    used = _lib.load().p3d_time_last_path().decode()
+    n_plan = nt * up
+    if path == "tma":
+        assert used == "tma", used
+    elif path == "pipeline":
+        assert used == "pipeline", used
+    else:
+        assert used == ("direct" if n_plan in (512, 1024, 2048, 4096, 2000, 4000) else "generic"), used
+    Fr, fr = tor.time_fft(x, twt, compute_real=real, **kw)
+    assert F.shape == Fr.shape and rel_l2(F, Fr) < 5e-6
+    np.testing.assert_allclose(f, fr)
+    nte = nt - (nt % 2)
+    Fin = np.fft.fftshift(F, axes=0) if not real else F
+    xb = timeaxis.time_ifft(Fin, synth.DT_MS, synth.T0_MS, compute_real=real, ascending=True, nt_out=nte)
+    used = _lib.load().p3d_time_last_path().decode()
+    # the inverse of a two-sided spectrum needs twice the stage: the pipeline takes it for the lengths whose tiles are two pairs wide
+    assert used == path or path == "direct" or (path == "tma" and not real and n_plan >= 2500 and used == "pipeline"), used
+    xr = tor.time_ifft(np.fft.fftshift(Fr, axes=0) if not real else Fr, synth.DT_MS, synth.T0_MS, compute_real=real)
+    assert rel_l2(xb, xr[:nte]) < 5e-6
+    if n_plan == nt:
+        assert rel_l2(xb, x[:nte]) < 5e-6
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases
 # ------------------------------------------------------------------------------------------------

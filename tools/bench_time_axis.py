@@ -38,7 +38,13 @@ def main():
     def inv():
         _lib.check(lib.p3d_time_ifft(0, C.c_void_p(dF.ptr), 1, C.c_void_p(dy.ptr), 1, nt, nt, ntr, dt, t0, real, 0))
 
-    for name, fn, nbytes in (("time_fft", fwd, x.nbytes + nf * ntr * 8), ("time_ifft", inv, x.nbytes + nf * ntr * 8)):
+    def env():
+        _lib.check(lib.p3d_time_envelope(0, C.c_void_p(dx.ptr), 1, C.c_void_p(dy.ptr), 1, nt, ntr))
+
+    cases = [("time_fft", fwd, x.nbytes + nf * ntr * 8), ("time_ifft", inv, x.nbytes + nf * ntr * 8)]
+    if os.environ.get("P3D_BENCH_ENVELOPE"):
+        cases = [("envelope", env, 2 * x.nbytes)]
+    for name, fn, nbytes in cases:
         fn(); fn()
         lib.p3d_device_synchronize(0)
         t = time.perf_counter()
@@ -48,7 +54,9 @@ def main():
         lib.p3d_device_synchronize(0)
         el = (time.perf_counter() - t) / reps
         kms = C.c_double(); lib.p3d_time_last_kernel_ms(C.byref(kms))
-        print(f"{name}: nt={nt} traces={ntr} real={real}: call {el*1e3:.2f} ms; kernels {kms.value:.2f} ms = {nbytes/max(kms.value,1e-9)/1e6:.0f} GB/s algorithmic ({nbytes/1e9:.1f} GB)")
+        print(f"{name}: nt={nt} traces={ntr} real={real}: call {el*1e3:.2f} ms; kernels {kms.value:.2f} ms = {nbytes/max(kms.value,1e-9)/1e6:.0f} GB/s algorithmic ({nbytes/1e9:.1f} GB) [{lib.p3d_time_last_path().decode()}]")
+    if os.environ.get("P3D_BENCH_ENVELOPE"):
+        return
     y = np.empty((nt, 64), np.float32)
     full = np.empty_like(x); dy.download(full)
     err = np.linalg.norm(full[:, :4096] - x[:, :4096]) / np.linalg.norm(x[:, :4096])
