@@ -309,6 +309,12 @@ k_time_fwd_tma(const __grid_constant__ TimeGeom G, const __grid_constant__ CUten
     int tile = blockIdx.x;
     issue(tile);
     for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        // opaque copy of the row pitch: the 2 E output row addresses are recomputed per tile instead of being hoisted out of
+        // the tile loop, where they would occupy 4 E registers for the whole kernel (spills)
+        long long ntr = G.ntr;
+        asm volatile("" : "+l"(ntr));
+        const Cx<float>* ph_t = phase;                    // likewise the E phase factors (loop-invariant loads)
+        asm volatile("" : "+l"(ph_t));
         if constexpr (TMA) mbar_wait(&bar, (unsigned)it & 1u);
         else { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncthreads(); }
         const float2* st = stage + c;
@@ -334,9 +340,9 @@ k_time_fwd_tma(const __grid_constant__ TimeGeom G, const __grid_constant__ CUten
                     const Cx<float> z1 = v[e], z2 = buf[km * C];
                     const Cx<float> xa = cmake<float>(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
                     const Cx<float> xb = cmake<float>(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
-                    const Cx<float> ph = phase[k];
+                    const Cx<float> ph = ph_t[k];
                     const Cx<float> fa = cmul(xa, ph), fb = cmul(xb, ph);
-                    __stcs(reinterpret_cast<float4*>(F + (long long)k * G.ntr + tr), make_float4(fa.x, fa.y, fb.x, fb.y));
+                    __stcs(reinterpret_cast<float4*>(F + (long long)k * ntr + tr), make_float4(fa.x, fa.y, fb.x, fb.y));
                 }
             }
         }
@@ -387,6 +393,12 @@ k_time_inv_tma(const __grid_constant__ TimeGeom G, const __grid_constant__ CUten
     int tile = blockIdx.x;
     issue(tile);
     for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        // opaque copy of the row pitch: the 2 E output row addresses are recomputed per tile instead of being hoisted out of
+        // the tile loop, where they would occupy 4 E registers for the whole kernel (spills)
+        long long ntr = G.ntr;
+        asm volatile("" : "+l"(ntr));
+        const Cx<float>* ph_t = phase;                    // likewise the E phase factors (loop-invariant loads)
+        asm volatile("" : "+l"(ph_t));
         if constexpr (TMA) mbar_wait(&bar, (unsigned)it & 1u);
         else { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncthreads(); }
         const float4* st = stage + c;
@@ -400,14 +412,14 @@ k_time_inv_tma(const __grid_constant__ TimeGeom G, const __grid_constant__ CUten
                 // irfft semantics: bins 0..N/2 given, the rest is their conjugate mirror; imaginary part of DC / Nyquist ignored
                 const int kk = (k <= half) ? k : km;
                 const float4 p = st[kk * C];
-                const Cx<float> ph = phase[kk];
+                const Cx<float> ph = ph_t[kk];
                 ha = cmul(cmake<float>(p.x, p.y), ph); hb = cmul(cmake<float>(p.z, p.w), ph);
                 if (k > half) { ha.y = -ha.y; hb.y = -hb.y; }
                 if (k == 0 || k == half) { ha.y = 0.f; hb.y = 0.f; }
             } else {
                 const int r1 = shifted ? (k + half) % N : k, r2 = shifted ? (km + half) % N : km;
                 const float4 p = st[r1 * C], q = st[r2 * C];
-                const Cx<float> ph1 = phase[k], ph2 = phase[km];
+                const Cx<float> ph1 = ph_t[k], ph2 = ph_t[km];
                 const Cx<float> ga = cmul(cmake<float>(p.x, p.y), ph1), gb = cmul(cmake<float>(p.z, p.w), ph1);
                 const Cx<float> a2 = cmul(cmake<float>(q.x, q.y), ph2), b2 = cmul(cmake<float>(q.z, q.w), ph2);
                 ha = cmake<float>(0.5f * (ga.x + a2.x), 0.5f * (ga.y - a2.y));
@@ -423,7 +435,203 @@ k_time_inv_tma(const __grid_constant__ TimeGeom G, const __grid_constant__ CUten
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int n = j + e * T;
-                if (n < G.nt) __stcs(reinterpret_cast<float2*>(x + (long long)n * G.ntr + tr), make_float2(v[e].x, v[e].y));
+                if (n < G.nt) __stcs(reinterpret_cast<float2*>(x + (long long)n * ntr + tr), make_float2(v[e].x, v[e].y));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-pass kernels for the long records (2048 / 4096 / 2000 / 4000 samples): N = 2 H, two H-point
+// register transforms per line and one radix-2 step between them.  A thread then holds only H / T
+// values at a time, so a CTA of the same size covers TWICE as many traces as the N-point plan
+// could - 16 traces of 2048 samples: 64-byte rows on the way in, 128-byte rows on the way out -,
+// and the row width of the strided tile is what the time-axis kernels are bound by (8 / 16 / 32 /
+// 64 / 128 bytes per row: 0.7 / 1.2 / 2.0 / 3.2 / 4.5 TB/s, profiles/r2_time_axis_tile_width.txt).
+//   forward (decimation in time):  Ze = FFT_H(z[2m]), Zo = FFT_H(z[2m+1]);  Z[k] = Ze[k] + w^k Zo[k],
+//                                  Z[k+H] = Ze[k] - w^k Zo[k],  w = exp(-2 pi i / N)
+//   inverse (decimation in frequency):  x[2m] = IFFT_H(P[k] + P[k+H]),  x[2m+1] = IFFT_H((P[k] - P[k+H]) conj(w^k))
+// wsplit: w^k, k < H.
+// ------------------------------------------------------------------------------------------------
+template <typename LPH, int C>
+__global__ void __launch_bounds__(LPH::T* C, 1)
+k_time_fwd_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUtensorMap tmap, const Cx<float>* __restrict__ tw,
+                 const Cx<float>* __restrict__ wsplit, Cx<float>* __restrict__ F, const Cx<float>* __restrict__ phase,
+                 const int ntiles, const int box_rows, const int stage_rows) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    __shared__ unsigned long long bar;
+    unsigned char* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    constexpr int E = LPH::E, T = LPH::T, H = LPH::N;
+    const int STAGE = stage_rows * C;
+    float2* stage = reinterpret_cast<float2*>(smem_raw);                    // [stage_rows >= 2H][C] trace pairs
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    ColAcc1<float, C, LPH::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw + (size_t)STAGE * sizeof(float2)) + c;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    auto issue = [&](int tile) {
+        if (tid == 0 && tile < ntiles) {
+            mbar_expect_tx(&bar, (unsigned)(STAGE * sizeof(float2)));
+            for (int r0 = 0; r0 < stage_rows; r0 += box_rows) tma_load_3d(stage + (size_t)r0 * C, &tmap, tile * C, r0, 0, &bar);
+        }
+    };
+    const bool two_sided = G.nf > H + 1;
+    int tile = blockIdx.x;
+    issue(tile);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        // opaque copy of the row pitch: the 2 E output row addresses are recomputed per tile instead of being hoisted out of
+        // the tile loop, where they would occupy 4 E registers for the whole kernel (spills)
+        long long ntr = G.ntr;
+        asm volatile("" : "+l"(ntr));
+        const Cx<float>* ph_t = phase;                    // likewise the E phase factors (loop-invariant loads)
+        asm volatile("" : "+l"(ph_t));
+        mbar_wait(&bar, (unsigned)it & 1u);
+        float2* st = stage + c;
+        const Cx<float>* ws_t = wsplit;
+        asm volatile("" : "+l"(ws_t));
+        Cx<float> lo[E], hi[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const float2 p = st[(2 * (j + e * T)) * C]; lo[e] = cmake<float>(p.x, p.y); }
+        LPH::template fft<-1, 0, float>(lo, acc, j, tw);
+        // park Ze[k] in the slots this thread has just emptied (row 2k of its own column)
+#pragma unroll
+        for (int e = 0; e < E; ++e) st[(2 * (j + e * T)) * C] = make_float2(lo[e].x, lo[e].y);
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const float2 p = st[(2 * (j + e * T) + 1) * C]; hi[e] = cmake<float>(p.x, p.y); }
+        LPH::template fft<-1, 0, float>(hi, acc, j, tw);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = j + e * T;
+            const float2 p = st[(2 * k) * C];
+            const Cx<float> t = cmul(hi[e], ws_t[k]);
+            lo[e] = cmake<float>(p.x + t.x, p.y + t.y);          // Z[k]
+            hi[e] = cmake<float>(p.x - t.x, p.y - t.y);          // Z[k + H]
+        }
+        __syncthreads();                                  // the stage is free: the next tile arrives during the epilogue
+        issue(tile + gridDim.x);
+        // separate the two real traces: rows k <= H need Z[N - k] = Z[(H - k) + H], the upper value of another thread
+        Cx<float>* buf = acc.line(0);
+#pragma unroll
+        for (int e = 0; e < E; ++e) buf[(j + e * T) * C] = hi[e];
+        __syncthreads();
+        const long long tr = (long long)tile * 2 * C + 2 * c;
+        const bool ok = tr < G.ntr;
+        auto emit = [&](int row, Cx<float> z1, Cx<float> z2) {
+            const Cx<float> xa = cmake<float>(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+            const Cx<float> xb = cmake<float>(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+            const Cx<float> ph = ph_t[row];
+            const Cx<float> fa = cmul(xa, ph), fb = cmul(xb, ph);
+            __stcs(reinterpret_cast<float4*>(F + (long long)row * ntr + tr), make_float4(fa.x, fa.y, fb.x, fb.y));
+        };
+        if (ok) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int k = j + e * T;
+                if (k == 0) { emit(0, lo[e], lo[e]); emit(H, hi[e], hi[e]); }
+                else emit(k, lo[e], buf[(H - k) * C]);
+            }
+        }
+        if (two_sided) {
+            // rows k + H (k >= 1) need Z[N - k - H] = Z[H - k], the lower value of another thread
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; ++e) buf[(j + e * T) * C] = lo[e];
+            __syncthreads();
+            if (ok) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int k = j + e * T;
+                    if (k > 0) emit(k + H, hi[e], buf[(H - k) * C]);
+                }
+            }
+        }
+    }
+}
+
+// inverse of a one-sided spectrum (compute_real): the stage holds rows 0 .. H of the tile, [row][C] pairs of complex64
+template <typename LPH, int C>
+__global__ void __launch_bounds__(LPH::T* C, 1)
+k_time_inv_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUtensorMap tmap, const Cx<float>* __restrict__ tw,
+                 const Cx<float>* __restrict__ wsplit, float* __restrict__ x, const Cx<float>* __restrict__ phase,
+                 const int ntiles, const int box_rows, const int stage_rows) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    __shared__ unsigned long long bar;
+    unsigned char* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    constexpr int E = LPH::E, T = LPH::T, H = LPH::N;
+    const int STAGE = stage_rows * C;
+    float4* stage = reinterpret_cast<float4*>(smem_raw);                    // [stage_rows >= H + 1][C]
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    ColAcc1<float, C, LPH::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw + (size_t)STAGE * sizeof(float4)) + c;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    auto issue = [&](int tile) {
+        if (tid == 0 && tile < ntiles) {
+            mbar_expect_tx(&bar, (unsigned)(STAGE * sizeof(float4)));
+            for (int r0 = 0; r0 < stage_rows; r0 += box_rows) tma_load_3d(stage + (size_t)r0 * C, &tmap, tile * C * 2, r0, 0, &bar);
+        }
+    };
+    int tile = blockIdx.x;
+    issue(tile);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        // opaque copy of the row pitch: the 2 E output row addresses are recomputed per tile instead of being hoisted out of
+        // the tile loop, where they would occupy 4 E registers for the whole kernel (spills)
+        long long ntr = G.ntr;
+        asm volatile("" : "+l"(ntr));
+        const Cx<float>* ph_t = phase;                    // likewise the E phase factors (loop-invariant loads)
+        asm volatile("" : "+l"(ph_t));
+        mbar_wait(&bar, (unsigned)it & 1u);
+        const float4* st = stage + c;
+        const Cx<float>* ws_t = wsplit;
+        asm volatile("" : "+l"(ws_t));
+        // packed Hermitian spectrum P = ha + i hb of the trace pair at bins k and k + H (k < H):
+        //   P[k]     from row k (imaginary parts of DC ignored),
+        //   P[k + H] from row H (k = 0, imaginary parts of Nyquist ignored) or the conjugate mirror of row H - k
+        auto bins = [&](int k, Cx<float>& p0, Cx<float>& p1) {
+            const float4 a = st[k * C];
+            const Cx<float> ph = ph_t[k];
+            Cx<float> ha = cmul(cmake<float>(a.x, a.y), ph), hb = cmul(cmake<float>(a.z, a.w), ph);
+            if (k == 0) { ha.y = 0.f; hb.y = 0.f; }
+            p0 = cmake<float>(ha.x - hb.y, ha.y + hb.x);
+            const int km = H - k;                                   // k = 0: row H itself
+            const float4 b = st[km * C];
+            const Cx<float> pm = ph_t[km];
+            Cx<float> ma = cmul(cmake<float>(b.x, b.y), pm), mb = cmul(cmake<float>(b.z, b.w), pm);
+            if (k == 0) { ma.y = 0.f; mb.y = 0.f; } else { ma.y = -ma.y; mb.y = -mb.y; }
+            p1 = cmake<float>(ma.x - mb.y, ma.y + mb.x);
+        };
+        const long long tr = (long long)tile * 2 * C + 2 * c;
+        const bool ok = tr < G.ntr;
+        Cx<float> v[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            Cx<float> p0, p1; bins(j + e * T, p0, p1); v[e] = cmake<float>(p0.x + p1.x, p0.y + p1.y);
+            if (e % 4 == 3) __syncwarp();          // scheduling fence: the loads of at most four bins in flight (registers)
+        }
+        LPH::template fft<+1, 0, float>(v, acc, j, tw);
+        if (ok) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int n = 2 * (j + e * T);
+                if (n < G.nt) __stcs(reinterpret_cast<float2*>(x + (long long)n * ntr + tr), make_float2(v[e].x, v[e].y));
+            }
+        }
+        asm volatile("" : "+l"(ph_t));                    // second pass: reload instead of keeping 2 E factors across the transform
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = j + e * T;
+            Cx<float> p0, p1; bins(k, p0, p1);
+            v[e] = cmulc(cmake<float>(p0.x - p1.x, p0.y - p1.y), ws_t[k]);
+            if (e % 4 == 3) __syncwarp();
+        }
+        __syncthreads();                                  // the stage is free: the next tile arrives during the second transform
+        issue(tile + gridDim.x);
+        LPH::template fft<+1, 0, float>(v, acc, j, tw);
+        if (ok) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int n = 2 * (j + e * T) + 1;
+                if (n < G.nt) __stcs(reinterpret_cast<float2*>(x + (long long)n * ntr + tr), make_float2(v[e].x, v[e].y));
             }
         }
     }
@@ -875,7 +1083,73 @@ bool launch_time_tma(const TimeGeom& G0, const void* din, void* dout, const Cx<f
     return true;
 }
 
+template <typename LPH, int C>
+bool launch_time_split(const TimeGeom& G0, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
+    constexpr int H = LPH::N;
+    if (G0.nfft != 2 * H || G0.ntr % 4 != 0) return false;
+    if (inverse && !G0.compute_real) return false;                       // a two-sided spectrum does not fit the stage
+    if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
+    TimeGeom G = G0; G.C = C;
+    const long long tiles = (G.ntr + 2 * C - 1) / (2 * C);
+    if (tiles > 2147483647LL / (4 * C)) return false;
+    int box_rows, stage_rows;
+    size_t stage_bytes;
+    if (!inverse) { pick_box(2 * H, C * (int)sizeof(float2), &box_rows, &stage_rows); stage_bytes = (size_t)stage_rows * C * sizeof(float2); }
+    else          { pick_box(H + 1, C * (int)sizeof(float4), &box_rows, &stage_rows); stage_bytes = (size_t)stage_rows * C * sizeof(float4); }
+    const size_t smem = stage_bytes + (size_t)LPH::LINE * C * sizeof(Cx<float>) + 128;
+    if (smem > smem_optin - 1024) return false;
+    CUtensorMap map;
+    if (!inverse) { if (!tma_encode_tile_map(&map, din, 1, (int)G.nt, (int)(G.ntr / 2), 8, C, box_rows)) return false; }
+    else          { if (!tma_encode_tile_map(&map, din, 1, (int)G.nf, (int)(G.ntr / 2), 16, C, box_rows)) return false; }
+    std::vector<int> rad(LPH::NPASS);
+    LPH::radices(rad.data());
+    std::vector<Cx<float>> t = spec_twiddle_table(rad);
+    const size_t woff = (t.size() + 1) & ~(size_t)1;
+    t.resize(woff + H);
+    for (int k = 0; k < H; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)(2 * H);
+        t[woff + k] = cmake<float>((float)cos(a), (float)sin(a));
+    }
+    Cx<float>* d_tw = nullptr;
+    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
+    struct Free { Cx<float>* p; cudaEvent_t a, b; ~Free() { cudaFree(p); if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } fr{d_tw, nullptr, nullptr};
+    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    int dev = 0, sms = 0;
+    P3D_CUDA(cudaGetDevice(&dev));
+    P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char* g = getenv("P3D_TIME_GRID")) sms = std::max(1, atoi(g));
+    const unsigned grid = (unsigned)std::min<long long>(tiles, sms);
+    P3D_CUDA(cudaEventCreate(&fr.a)); P3D_CUDA(cudaEventCreate(&fr.b));
+    P3D_CUDA(cudaEventRecord(fr.a, 0));
+    if (!inverse) {
+        P3D_CUDA(cudaFuncSetAttribute(k_time_fwd_split<LPH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_time_fwd_split<LPH, C><<<grid, LPH::T * C, smem>>>(G, map, d_tw, d_tw + woff, (Cx<float>*)dout, d_ph, (int)tiles, box_rows, stage_rows);
+    } else {
+        P3D_CUDA(cudaFuncSetAttribute(k_time_inv_split<LPH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_time_inv_split<LPH, C><<<grid, LPH::T * C, smem>>>(G, map, d_tw, d_tw + woff, (float*)dout, d_ph, (int)tiles, box_rows, stage_rows);
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaEventRecord(fr.b, 0));
+    P3D_CUDA(cudaDeviceSynchronize());
+    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.a, fr.b); g_last_kernel_ms = ms; g_last_path = "tma"; }
+    return true;
+}
+
+bool try_time_split(const TimeGeom& G, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
+    switch (G.nfft) {
+        case 2048: return launch_time_split<TP1024, 8>(G, din, dout, d_ph, inverse, smem_optin);
+        case 4096: return launch_time_split<TP2048, 4>(G, din, dout, d_ph, inverse, smem_optin);
+        case 2000: return launch_time_split<TP1000, 8>(G, din, dout, d_ph, inverse, smem_optin);
+        case 4000: return launch_time_split<TP2000, 4>(G, din, dout, d_ph, inverse, smem_optin);
+        default: return false;
+    }
+}
+
 bool try_time_tma(const TimeGeom& G, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
+    {
+        const char* sp = getenv("P3D_TIME_SPLIT");                      // experiments: 0 = N-point plans for the long records too
+        if (!(sp && atoi(sp) == 0) && try_time_split(G, din, dout, d_ph, inverse, smem_optin)) return true;
+    }
     // the inverse of a two-sided spectrum stages nfft rows of 16 bytes per trace pair: half the tile width if that is too much
     const bool narrow = inverse && !G.compute_real;
 #define P3D_TIME_TMA(LP, C, TMA) \
@@ -926,19 +1200,23 @@ bool try_time_direct(const TimeGeom& G, const void* din, void* dout, const Cx<fl
     }
 }
 
-// Which implementation first (B200, 10^6 traces, profiles/r2_time_axis_paths.txt): tiles of >= 64 bytes per time sample
-// (record lengths up to 1024) run fastest through the one-pass TMA kernels (3.1 - 4.5 TB/s algorithmic); with 2048 and
-// more samples a tile is only 16 - 32 bytes wide and the direct register kernels win (2.05 TB/s); the transposing
-// pipeline (1.3 TB/s for every length) takes what the others decline (odd trace counts, unaligned buffers).
+// Which implementation first (B200, 10^6 traces, profiles/r2_time_axis_paths_v2.txt): the one-pass TMA kernels - N-point
+// plans up to 1024 samples (3.1 - 4.5 TB/s algorithmic), the radix-2 split for 2048 / 4096 / 2000 / 4000 (2.5 - 2.9 TB/s
+// forward, 1.7 - 2.8 inverse); the direct register kernels (2.0 TB/s; tiles half as wide) for the inverse of a two-sided
+// spectrum of a long record, which does not fit the stage, and for trace counts that are even but not divisible by 4; the
+// transposing pipeline (1.3 TB/s for every length) takes what the others decline (odd trace counts, unaligned buffers).
 // P3D_TIME_PATH = tma | direct | pipeline overrides the first choice (read at every call; used by the tests).
 bool try_time_spec(const TimeGeom& G, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
     const char* path = getenv("P3D_TIME_PATH");
-    int first = (G.nfft == 2048 || G.nfft == 4096 || G.nfft == 2000 || G.nfft == 4000) ? 1 : 0;          // 0 one pass, 1 direct, 2 pipeline
+    const bool long_record = G.nfft == 2048 || G.nfft == 4096 || G.nfft == 2000 || G.nfft == 4000;
+    int first = (long_record && inverse && !G.compute_real) ? 1 : 0;          // 0 one pass, 1 direct, 2 pipeline
     if (getenv("P3D_TIME_DIRECT") || (path && !strcmp(path, "direct"))) first = 1;
     else if (path && !strcmp(path, "tma")) first = 0;
     else if (path && !strcmp(path, "pipeline")) first = 2;
-    if (first == 0 && try_time_tma(G, din, dout, d_ph, inverse, smem_optin)) return true;
-    if (first == 1) {
+    if (first == 0) {
+        if (try_time_tma(G, din, dout, d_ph, inverse, smem_optin)) return true;
+        if (!path && try_time_direct(G, din, dout, d_ph, inverse, smem_optin)) return true;
+    } else if (first == 1) {
         if (try_time_direct(G, din, dout, d_ph, inverse, smem_optin)) return true;
         if (path && !strcmp(path, "direct")) return false;                         // forced: the generic kernels take over
         if (try_time_tma(G, din, dout, d_ph, inverse, smem_optin)) return true;

@@ -14,8 +14,8 @@ from pseudo_3d_interpolation_b200 import _lib      # noqa: E402
 
 a = sys.argv[1:]
 nt = int(a[0]) if len(a) > 0 else 2048
-n1 = int(a[1]) if len(a) > 1 else 600
-n2 = int(a[2]) if len(a) > 2 else 600
+n1 = int(a[1]) if len(a) > 1 else 1000
+n2 = int(a[2]) if len(a) > 2 else 1000
 lib = _lib.load()
 _lib.require_gpu()
 ntr = n1 * n2
@@ -26,8 +26,11 @@ x = np.tile(blk, (1, (ntr + 4095) // 4096))[:, :ntr].copy()
 dx = _lib.DeviceBuffer(x.nbytes); dx.upload(x)
 dF = _lib.DeviceBuffer(nf * ntr * 8)
 dy = _lib.DeviceBuffer(x.nbytes)
-for path, asyn in (("direct", None), ("tma", "1"), ("tma", "0"), ("pipeline", None)):
-    os.environ["P3D_TIME_PATH"] = path
+for path, asyn in ((None, None), ("direct", None), ("pipeline", None)):
+    if path is None:
+        os.environ.pop("P3D_TIME_PATH", None)
+    else:
+        os.environ["P3D_TIME_PATH"] = path
     if asyn is None:
         os.environ.pop("P3D_TIME_ASYNC", None)
     else:
