@@ -519,12 +519,12 @@ def main():
                 _lib.check(fn()); _lib.check(fn())
                 ms = C.c_double(); lib.p3d_time_last_kernel_ms(C.byref(ms))
                 nbytes = xt.numel() * 4 + ft.numel() * 8
-                res[name] = {"kernel_ms": ms.value, "algorithmic_GBps": nbytes / max(ms.value, 1e-9) / 1e6}
+                res[name] = {"kernel_ms": ms.value, "algorithmic_GBps": nbytes / max(ms.value, 1e-9) / 1e6, "path": lib.p3d_time_last_path().decode()}
             et = torch.empty_like(xt)
             fn = lambda: lib.p3d_time_envelope(local, C.c_void_p(xt.data_ptr()), 1, C.c_void_p(et.data_ptr()), 1, nt_, ntr_)   # noqa: E731
             _lib.check(fn()); _lib.check(fn())
             ms = C.c_double(); lib.p3d_time_last_kernel_ms(C.byref(ms))
-            res["envelope"] = {"kernel_ms": ms.value, "algorithmic_GBps": 2 * xt.numel() * 4 / max(ms.value, 1e-9) / 1e6}
+            res["envelope"] = {"kernel_ms": ms.value, "algorithmic_GBps": 2 * xt.numel() * 4 / max(ms.value, 1e-9) / 1e6, "path": lib.p3d_time_last_path().decode()}
             del et
             res["sample"] = f"{nt_} samples x {ntr_} traces, compute_real"
             extras["time_axis"] = res

@@ -134,14 +134,16 @@ int p3d_time_ifft(int device, const void* x, int x_mem, float* out, int out_mem,
 
 /* Amplitude envelope along the time axis: env = |x + i Hilbert(x)|, the arithmetic of functions/signal.py:672-690
  * (scipy.signal.hilbert + abs) used by step 11 (cube_preprocessing_3D.py:341-353) to make the `env` variable.
- *   x, out : (nt, n_traces) float32, time-major; any nt (register-resident pipeline for 512/1024/2048/4096) */
+ *   x, out : (nt, n_traces) float32, time-major; any nt (register plans for 512 / 1000 / 1024 / 2000 / 2048 / 2500 /
+ *            3000 / 4000 / 4096 / 5000 samples, generic kernels otherwise) */
 int p3d_time_envelope(int device, const float* x, int x_mem, float* out, int out_mem, int64_t nt, int64_t n_traces);
 
 /* Device time (CUDA events) spent in the kernels of this thread's last p3d_time_fft / p3d_time_ifft
  * call (0 when the call used the generic direct kernels). */
 int p3d_time_last_kernel_ms(double* ms);
 /* Which kernels served this thread's last p3d_time_* call: "tma" (one pass: TMA-staged tiles, register FFT; record
- * lengths 512 / 1000 / 1024 / 2000 / 2048 / 2500 / 4000 / 4096 with a trace count divisible by 4), "pipeline"
+ * lengths 512 / 1000 / 1024 / 2000 / 2048 / 2500 / 4000 / 4096 with a trace count divisible by 4 and 16-byte aligned
+ * device buffers; 2048 / 4096 / 2000 / 4000 as two half-length transforms and a radix-2 step), "pipeline"
  * (transpose / FFT / transpose through L2), "direct" or "generic" (any length).  Environment: P3D_TIME_PATH =
  * tma | pipeline | direct selects the first candidate (read at every call). */
 const char* p3d_time_last_path(void);
