@@ -919,6 +919,81 @@ k_time_env_tma(const __grid_constant__ TimeGeom G, const __grid_constant__ CUten
     }
 }
 
+// envelope of the long records with the same radix-2 split: forward as in k_time_fwd_split, the Hilbert weights on
+// Z[k] and Z[k + H] (both held by the same thread), then the decimation-in-frequency inverse - no exchange between the
+// two directions.  The samples stay in the stage for the magnitude, so the half-spectra wait in registers (and partly in
+// local memory) instead of being parked there, and the next tile is requested only when this one is finished.
+template <typename LPH, int C>
+__global__ void __launch_bounds__(LPH::T* C, 1)
+k_time_env_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUtensorMap tmap, const Cx<float>* __restrict__ tw,
+                 const Cx<float>* __restrict__ wsplit, float* __restrict__ env, const int ntiles, const int box_rows, const int stage_rows) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    __shared__ unsigned long long bar;
+    unsigned char* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    constexpr int E = LPH::E, T = LPH::T, H = LPH::N;
+    const int STAGE = stage_rows * C;
+    float2* stage = reinterpret_cast<float2*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int c = tid % C, j = tid / C;
+    ColAcc1<float, C, LPH::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw + (size_t)STAGE * sizeof(float2)) + c;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    auto issue = [&](int tile) {
+        if (tid == 0 && tile < ntiles) {
+            mbar_expect_tx(&bar, (unsigned)(STAGE * sizeof(float2)));
+            for (int r0 = 0; r0 < stage_rows; r0 += box_rows) tma_load_3d(stage + (size_t)r0 * C, &tmap, tile * C, r0, 0, &bar);
+        }
+    };
+    const float inv_n = 1.f / (float)(2 * H);
+    int tile = blockIdx.x;
+    issue(tile);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        long long ntr = G.ntr;
+        asm volatile("" : "+l"(ntr));
+        const Cx<float>* ws_t = wsplit;
+        asm volatile("" : "+l"(ws_t));
+        mbar_wait(&bar, (unsigned)it & 1u);
+        const float2* st = stage + c;
+        Cx<float> lo[E], hi[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const float2 p = st[(2 * (j + e * T)) * C]; lo[e] = cmake<float>(p.x, p.y); }
+        LPH::template fft<-1, 0, float>(lo, acc, j, tw);
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const float2 p = st[(2 * (j + e * T) + 1) * C]; hi[e] = cmake<float>(p.x, p.y); }
+        LPH::template fft<-1, 0, float>(hi, acc, j, tw);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = j + e * T;
+            const Cx<float> w = ws_t[k];
+            const Cx<float> t = cmul(hi[e], w);
+            const Cx<float> z0 = cmake<float>(lo[e].x + t.x, lo[e].y + t.y);          // Z[k]
+            const Cx<float> z1 = cmake<float>(lo[e].x - t.x, lo[e].y - t.y);          // Z[k + H]
+            // -i sgn z / N: + below Nyquist (bin k), - above (bin k + H), 0 at DC and Nyquist (k = 0)
+            const float sg = (k == 0) ? 0.f : inv_n;
+            const Cx<float> p0 = cmake<float>(sg * z0.y, -sg * z0.x);
+            const Cx<float> p1 = cmake<float>(-sg * z1.y, sg * z1.x);
+            lo[e] = cmake<float>(p0.x + p1.x, p0.y + p1.y);
+            hi[e] = cmulc(cmake<float>(p0.x - p1.x, p0.y - p1.y), w);
+        }
+        LPH::template fft<+1, 0, float>(lo, acc, j, tw);
+        LPH::template fft<+1, 0, float>(hi, acc, j, tw);
+        const long long tr = (long long)tile * 2 * C + 2 * c;
+        if (tr < G.ntr) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int n = 2 * (j + e * T);
+                const float2 p = st[n * C], q = st[(n + 1) * C];
+                __stcs(reinterpret_cast<float2*>(env + (long long)n * ntr + tr),
+                       make_float2(sqrtf(p.x * p.x + lo[e].x * lo[e].x), sqrtf(p.y * p.y + lo[e].y * lo[e].y)));
+                __stcs(reinterpret_cast<float2*>(env + (long long)(n + 1) * ntr + tr),
+                       make_float2(sqrtf(q.x * q.x + hi[e].x * hi[e].x), sqrtf(q.y * q.y + hi[e].y * hi[e].y)));
+            }
+        }
+        __syncthreads();
+        issue(tile + gridDim.x);
+    }
+}
+
 // device time of the kernels of the last p3d_time_fft / p3d_time_ifft call of this thread
 static thread_local double g_last_kernel_ms = 0.0;
 // which kernels served it: "tma" (one pass, TMA-staged), "pipeline" (transpose / FFT / transpose), "direct", "generic"
@@ -1296,10 +1371,67 @@ bool launch_env_tma(const TimeGeom& G0, const float* din, float* dout, size_t sm
     return true;
 }
 
+template <typename LPH, int C>
+bool launch_env_split(const TimeGeom& G0, const float* din, float* dout, size_t smem_optin) {
+    constexpr int H = LPH::N;
+    if (G0.nfft != 2 * H || G0.ntr % 4 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
+    TimeGeom G = G0; G.C = C;
+    const long long tiles = (G.ntr + 2 * C - 1) / (2 * C);
+    if (tiles > 2147483647LL / (4 * C)) return false;
+    int box_rows, stage_rows;
+    pick_box(2 * H, C * (int)sizeof(float2), &box_rows, &stage_rows);
+    const size_t smem = (size_t)stage_rows * C * sizeof(float2) + (size_t)LPH::LINE * C * sizeof(Cx<float>) + 128;
+    if (smem > smem_optin - 1024) return false;
+    CUtensorMap map;
+    if (!tma_encode_tile_map(&map, din, 1, (int)G.nt, (int)(G.ntr / 2), 8, C, box_rows)) return false;
+    std::vector<int> rad(LPH::NPASS);
+    LPH::radices(rad.data());
+    std::vector<Cx<float>> t = spec_twiddle_table(rad);
+    const size_t woff = (t.size() + 1) & ~(size_t)1;
+    t.resize(woff + H);
+    for (int k = 0; k < H; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)(2 * H);
+        t[woff + k] = cmake<float>((float)cos(a), (float)sin(a));
+    }
+    Cx<float>* d_tw = nullptr;
+    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
+    struct Free { Cx<float>* p; cudaEvent_t a, b; ~Free() { cudaFree(p); if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } fr{d_tw, nullptr, nullptr};
+    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+    int dev = 0, sms = 0;
+    P3D_CUDA(cudaGetDevice(&dev));
+    P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char* g = getenv("P3D_TIME_GRID")) sms = std::max(1, atoi(g));
+    const unsigned grid = (unsigned)std::min<long long>(tiles, sms);
+    P3D_CUDA(cudaEventCreate(&fr.a)); P3D_CUDA(cudaEventCreate(&fr.b));
+    P3D_CUDA(cudaEventRecord(fr.a, 0));
+    P3D_CUDA(cudaFuncSetAttribute(k_time_env_split<LPH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_time_env_split<LPH, C><<<grid, LPH::T * C, smem>>>(G, map, d_tw, d_tw + woff, dout, (int)tiles, box_rows, stage_rows);
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaEventRecord(fr.b, 0));
+    P3D_CUDA(cudaDeviceSynchronize());
+    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.a, fr.b); g_last_kernel_ms = ms; g_last_path = "tma"; }
+    return true;
+}
+
 bool try_env_tma(const TimeGeom& G, const float* din, float* dout, size_t smem_optin) {
     const char* path = getenv("P3D_TIME_PATH");
     if (path && strcmp(path, "tma")) return false;
-    if (!path && G.nfft == 2048) return false;          // 2048 samples, 32-byte box rows: the pipeline is as fast (1.11 vs 1.09 TB/s)
+    {
+        const char* sp = getenv("P3D_TIME_SPLIT");
+        bool done = false;
+        if (!(sp && atoi(sp) == 0)) {
+            switch (G.nfft) {
+                case 2048: done = launch_env_split<TP1024, 8>(G, din, dout, smem_optin); break;
+                case 4096: done = launch_env_split<TP2048, 4>(G, din, dout, smem_optin); break;
+                case 2000: done = launch_env_split<TP1000, 8>(G, din, dout, smem_optin); break;
+                case 4000: done = launch_env_split<TP2000, 4>(G, din, dout, smem_optin); break;
+                default: break;
+            }
+        }
+        if (done) return true;
+    }
+    if (!path && G.nfft == 2048) return false;          // N-point plan at 2048 samples, 32-byte box rows: the pipeline is as fast
     switch (G.nfft) {
         case 512:  return launch_env_tma<TP512, 16>(G, din, dout, smem_optin);
         case 1024: return launch_env_tma<TP1024, 8>(G, din, dout, smem_optin);
