@@ -1100,113 +1100,109 @@ static void pick_box(int rows, int row_bytes, int* box_rows, int* stage_rows) {
     }
 }
 
+// What the one-pass launchers share: the checks, the stage and its TMA boxes, the tensor map, the tables on the device,
+// the grid (one persistent CTA per SM) and the CUDA events around the launch.
+struct OnePass {
+    TimeGeom G;
+    long long tiles = 0;
+    int box_rows = 0, stage_rows = 0;
+    size_t smem = 0;
+    unsigned grid = 0;
+    CUtensorMap map;
+    Cx<float>* d_tw = nullptr;            // twiddle tables of the plan [+ w^k, k < H, for the radix-2 split]
+    const Cx<float>* d_wsplit = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    OnePass() { memset(&map, 0, sizeof(map)); }
+    ~OnePass() { if (d_tw) cudaFree(d_tw); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+
+    // stage of `rows` rows of C elements (elem_bytes: 8 = a pair of samples, 16 = a pair of spectral values) cut out of a
+    // (map_rows, n_traces / 2) tensor at `src`; `line` = exchange-buffer elements per line.  false: this path declines.
+    bool setup(const TimeGeom& G0, const void* src, const void* dst, int C, int rows, long long map_rows, int elem_bytes, int line,
+               bool use_tma, size_t smem_optin) {
+        if (G0.ntr % 4 != 0) return false;                                   // 16-byte row pitch and whole trace pairs
+        if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return false;
+        G = G0; G.C = C;
+        tiles = (G.ntr + 2 * C - 1) / (2 * C);
+        if (tiles > 2147483647LL / (4 * C)) return false;
+        pick_box(rows, C * elem_bytes, &box_rows, &stage_rows);
+        if (!use_tma) stage_rows = rows;
+        smem = (size_t)stage_rows * C * elem_bytes + (size_t)line * C * sizeof(Cx<float>) + 128;
+        if (smem > smem_optin - 1024) return false;
+        if (use_tma && !tma_encode_tile_map(&map, src, 1, (int)map_rows, (int)(G.ntr / 2), elem_bytes, C, box_rows)) return false;
+        int dev = 0, sms = 0;
+        P3D_CUDA(cudaGetDevice(&dev));
+        P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (const char* g = getenv("P3D_TIME_GRID")) sms = std::max(1, atoi(g));          // tests: many tiles per CTA on small inputs
+        grid = (unsigned)std::min<long long>(tiles, sms);
+        return true;
+    }
+    void tables(const std::vector<int>& radices, int h_split) {
+        std::vector<Cx<float>> t = spec_twiddle_table(radices);
+        const size_t woff = (t.size() + 1) & ~(size_t)1;
+        if (h_split > 0) {
+            t.resize(woff + (size_t)h_split);
+            for (int k = 0; k < h_split; ++k) {
+                const double a = -2.0 * M_PI * (double)k / (double)(2 * h_split);
+                t[woff + k] = cmake<float>((float)cos(a), (float)sin(a));
+            }
+        }
+        P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
+        P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
+        d_wsplit = d_tw + woff;
+    }
+    template <typename K> void begin(K kernel) {
+        P3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        P3D_CUDA(cudaEventCreate(&e0)); P3D_CUDA(cudaEventCreate(&e1));
+        P3D_CUDA(cudaEventRecord(e0, 0));
+    }
+    void end() {
+        P3D_CUDA(cudaGetLastError());
+        P3D_CUDA(cudaEventRecord(e1, 0));
+        P3D_CUDA(cudaDeviceSynchronize());
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); g_last_kernel_ms = ms; g_last_path = "tma";
+    }
+};
+
+template <typename LP> std::vector<int> radices_of_plan() { std::vector<int> r(LP::NPASS); LP::radices(r.data()); return r; }
+
 template <typename LP, int C, bool TMA = true>
 bool launch_time_tma(const TimeGeom& G0, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
     if (const char* a = getenv("P3D_TIME_ASYNC")) {                     // experiments: 1 = cp.async copies, 0 = TMA
         if constexpr (TMA) { if (atoi(a) == 1) return launch_time_tma<LP, C, false>(G0, din, dout, d_ph, inverse, smem_optin); }
         else               { if (atoi(a) == 0) return launch_time_tma<LP, C, true>(G0, din, dout, d_ph, inverse, smem_optin); }
     }
-    if (G0.ntr % 4 != 0) return false;                                   // 16-byte row pitch and whole trace pairs
-    if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
-    TimeGeom G = G0; G.C = C;
-    const long long tiles = (G.ntr + 2 * C - 1) / (2 * C);
-    if (tiles > 2147483647LL / (4 * C)) return false;
-    int box_rows, stage_rows;
-    size_t stage_bytes;
+    OnePass op;
+    if (!inverse) { if (!op.setup(G0, din, dout, C, LP::N, G0.nt, (int)sizeof(float2), LP::LINE, TMA, smem_optin)) return false; }
+    else          { if (!op.setup(G0, din, dout, C, (int)G0.nf, G0.nf, (int)sizeof(float4), LP::LINE, TMA, smem_optin)) return false; }
+    op.tables(radices_of_plan<LP>(), 0);
     if (!inverse) {
-        pick_box(LP::N, C * (int)sizeof(float2), &box_rows, &stage_rows);
-        if (!TMA) stage_rows = LP::N;
-        stage_bytes = (size_t)stage_rows * C * sizeof(float2);
+        op.begin(k_time_fwd_tma<LP, C, TMA>);
+        k_time_fwd_tma<LP, C, TMA><<<op.grid, LP::T * C, op.smem>>>(op.G, op.map, op.d_tw, (const float*)din, (Cx<float>*)dout, d_ph, (int)op.tiles, op.box_rows, op.stage_rows);
     } else {
-        pick_box((int)G.nf, C * (int)sizeof(float4), &box_rows, &stage_rows);
-        if (!TMA) stage_rows = (int)G.nf;
-        stage_bytes = (size_t)stage_rows * C * sizeof(float4);
+        op.begin(k_time_inv_tma<LP, C, TMA>);
+        k_time_inv_tma<LP, C, TMA><<<op.grid, LP::T * C, op.smem>>>(op.G, op.map, op.d_tw, (const Cx<float>*)din, (float*)dout, d_ph, (int)op.tiles, op.box_rows, op.stage_rows);
     }
-    const size_t smem = stage_bytes + (size_t)LP::LINE * C * sizeof(Cx<float>) + 128;
-    if (smem > smem_optin - 1024) return false;
-    CUtensorMap map;
-    memset(&map, 0, sizeof(map));
-    if (TMA) {
-        if (!inverse) { if (!tma_encode_tile_map(&map, din, 1, (int)G.nt, (int)(G.ntr / 2), 8, C, box_rows)) return false; }
-        else          { if (!tma_encode_tile_map(&map, din, 1, (int)G.nf, (int)(G.ntr / 2), 16, C, box_rows)) return false; }
-    }
-    std::vector<int> rad(LP::NPASS);
-    LP::radices(rad.data());
-    std::vector<Cx<float>> t = spec_twiddle_table(rad);
-    Cx<float>* d_tw = nullptr;
-    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
-    struct Free { Cx<float>* p; cudaEvent_t a, b; ~Free() { cudaFree(p); if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } fr{d_tw, nullptr, nullptr};
-    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
-    int dev = 0, sms = 0;
-    P3D_CUDA(cudaGetDevice(&dev));
-    P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (const char* g = getenv("P3D_TIME_GRID")) sms = std::max(1, atoi(g));          // tests: many tiles per CTA on small inputs
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sms);
-    P3D_CUDA(cudaEventCreate(&fr.a)); P3D_CUDA(cudaEventCreate(&fr.b));
-    P3D_CUDA(cudaEventRecord(fr.a, 0));
-    if (!inverse) {
-        P3D_CUDA(cudaFuncSetAttribute(k_time_fwd_tma<LP, C, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_time_fwd_tma<LP, C, TMA><<<grid, LP::T * C, smem>>>(G, map, d_tw, (const float*)din, (Cx<float>*)dout, d_ph, (int)tiles, box_rows, stage_rows);
-    } else {
-        P3D_CUDA(cudaFuncSetAttribute(k_time_inv_tma<LP, C, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_time_inv_tma<LP, C, TMA><<<grid, LP::T * C, smem>>>(G, map, d_tw, (const Cx<float>*)din, (float*)dout, d_ph, (int)tiles, box_rows, stage_rows);
-    }
-    P3D_CUDA(cudaGetLastError());
-    P3D_CUDA(cudaEventRecord(fr.b, 0));
-    P3D_CUDA(cudaDeviceSynchronize());
-    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.a, fr.b); g_last_kernel_ms = ms; g_last_path = "tma"; }
+    op.end();
     return true;
 }
 
 template <typename LPH, int C>
 bool launch_time_split(const TimeGeom& G0, const void* din, void* dout, const Cx<float>* d_ph, bool inverse, size_t smem_optin) {
     constexpr int H = LPH::N;
-    if (G0.nfft != 2 * H || G0.ntr % 4 != 0) return false;
+    if (G0.nfft != 2 * H) return false;
     if (inverse && !G0.compute_real) return false;                       // a two-sided spectrum does not fit the stage
-    if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
-    TimeGeom G = G0; G.C = C;
-    const long long tiles = (G.ntr + 2 * C - 1) / (2 * C);
-    if (tiles > 2147483647LL / (4 * C)) return false;
-    int box_rows, stage_rows;
-    size_t stage_bytes;
-    if (!inverse) { pick_box(2 * H, C * (int)sizeof(float2), &box_rows, &stage_rows); stage_bytes = (size_t)stage_rows * C * sizeof(float2); }
-    else          { pick_box(H + 1, C * (int)sizeof(float4), &box_rows, &stage_rows); stage_bytes = (size_t)stage_rows * C * sizeof(float4); }
-    const size_t smem = stage_bytes + (size_t)LPH::LINE * C * sizeof(Cx<float>) + 128;
-    if (smem > smem_optin - 1024) return false;
-    CUtensorMap map;
-    if (!inverse) { if (!tma_encode_tile_map(&map, din, 1, (int)G.nt, (int)(G.ntr / 2), 8, C, box_rows)) return false; }
-    else          { if (!tma_encode_tile_map(&map, din, 1, (int)G.nf, (int)(G.ntr / 2), 16, C, box_rows)) return false; }
-    std::vector<int> rad(LPH::NPASS);
-    LPH::radices(rad.data());
-    std::vector<Cx<float>> t = spec_twiddle_table(rad);
-    const size_t woff = (t.size() + 1) & ~(size_t)1;
-    t.resize(woff + H);
-    for (int k = 0; k < H; ++k) {
-        const double a = -2.0 * M_PI * (double)k / (double)(2 * H);
-        t[woff + k] = cmake<float>((float)cos(a), (float)sin(a));
-    }
-    Cx<float>* d_tw = nullptr;
-    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
-    struct Free { Cx<float>* p; cudaEvent_t a, b; ~Free() { cudaFree(p); if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } fr{d_tw, nullptr, nullptr};
-    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
-    int dev = 0, sms = 0;
-    P3D_CUDA(cudaGetDevice(&dev));
-    P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (const char* g = getenv("P3D_TIME_GRID")) sms = std::max(1, atoi(g));
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sms);
-    P3D_CUDA(cudaEventCreate(&fr.a)); P3D_CUDA(cudaEventCreate(&fr.b));
-    P3D_CUDA(cudaEventRecord(fr.a, 0));
+    OnePass op;
+    if (!inverse) { if (!op.setup(G0, din, dout, C, 2 * H, G0.nt, (int)sizeof(float2), LPH::LINE, true, smem_optin)) return false; }
+    else          { if (!op.setup(G0, din, dout, C, H + 1, G0.nf, (int)sizeof(float4), LPH::LINE, true, smem_optin)) return false; }
+    op.tables(radices_of_plan<LPH>(), H);
     if (!inverse) {
-        P3D_CUDA(cudaFuncSetAttribute(k_time_fwd_split<LPH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_time_fwd_split<LPH, C><<<grid, LPH::T * C, smem>>>(G, map, d_tw, d_tw + woff, (Cx<float>*)dout, d_ph, (int)tiles, box_rows, stage_rows);
+        op.begin(k_time_fwd_split<LPH, C>);
+        k_time_fwd_split<LPH, C><<<op.grid, LPH::T * C, op.smem>>>(op.G, op.map, op.d_tw, op.d_wsplit, (Cx<float>*)dout, d_ph, (int)op.tiles, op.box_rows, op.stage_rows);
     } else {
-        P3D_CUDA(cudaFuncSetAttribute(k_time_inv_split<LPH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_time_inv_split<LPH, C><<<grid, LPH::T * C, smem>>>(G, map, d_tw, d_tw + woff, (float*)dout, d_ph, (int)tiles, box_rows, stage_rows);
+        op.begin(k_time_inv_split<LPH, C>);
+        k_time_inv_split<LPH, C><<<op.grid, LPH::T * C, op.smem>>>(op.G, op.map, op.d_tw, op.d_wsplit, (float*)dout, d_ph, (int)op.tiles, op.box_rows, op.stage_rows);
     }
-    P3D_CUDA(cudaGetLastError());
-    P3D_CUDA(cudaEventRecord(fr.b, 0));
-    P3D_CUDA(cudaDeviceSynchronize());
-    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.a, fr.b); g_last_kernel_ms = ms; g_last_path = "tma"; }
+    op.end();
     return true;
 }
 
@@ -1337,80 +1333,25 @@ bool launch_env_pipeline(const TimeGeom& G, const float* din, float* dout, size_
 
 template <typename LP, int C>
 bool launch_env_tma(const TimeGeom& G0, const float* din, float* dout, size_t smem_optin) {
-    if (G0.ntr % 4 != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
-    TimeGeom G = G0; G.C = C;
-    const long long tiles = (G.ntr + 2 * C - 1) / (2 * C);
-    if (tiles > 2147483647LL / (4 * C)) return false;
-    int box_rows, stage_rows;
-    pick_box(LP::N, C * (int)sizeof(float2), &box_rows, &stage_rows);
-    const size_t smem = (size_t)stage_rows * C * sizeof(float2) + (size_t)LP::LINE * C * sizeof(Cx<float>) + 128;
-    if (smem > smem_optin - 1024) return false;
-    CUtensorMap map;
-    if (!tma_encode_tile_map(&map, din, 1, (int)G.nt, (int)(G.ntr / 2), 8, C, box_rows)) return false;
-    std::vector<int> rad(LP::NPASS);
-    LP::radices(rad.data());
-    std::vector<Cx<float>> t = spec_twiddle_table(rad);
-    Cx<float>* d_tw = nullptr;
-    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
-    struct Free { Cx<float>* p; cudaEvent_t a, b; ~Free() { cudaFree(p); if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } fr{d_tw, nullptr, nullptr};
-    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
-    int dev = 0, sms = 0;
-    P3D_CUDA(cudaGetDevice(&dev));
-    P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (const char* g = getenv("P3D_TIME_GRID")) sms = std::max(1, atoi(g));
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sms);
-    P3D_CUDA(cudaEventCreate(&fr.a)); P3D_CUDA(cudaEventCreate(&fr.b));
-    P3D_CUDA(cudaEventRecord(fr.a, 0));
-    P3D_CUDA(cudaFuncSetAttribute(k_time_env_tma<LP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_time_env_tma<LP, C><<<grid, LP::T * C, smem>>>(G, map, d_tw, dout, (int)tiles, box_rows, stage_rows);
-    P3D_CUDA(cudaGetLastError());
-    P3D_CUDA(cudaEventRecord(fr.b, 0));
-    P3D_CUDA(cudaDeviceSynchronize());
-    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.a, fr.b); g_last_kernel_ms = ms; g_last_path = "tma"; }
+    OnePass op;
+    if (!op.setup(G0, din, dout, C, LP::N, G0.nt, (int)sizeof(float2), LP::LINE, true, smem_optin)) return false;
+    op.tables(radices_of_plan<LP>(), 0);
+    op.begin(k_time_env_tma<LP, C>);
+    k_time_env_tma<LP, C><<<op.grid, LP::T * C, op.smem>>>(op.G, op.map, op.d_tw, dout, (int)op.tiles, op.box_rows, op.stage_rows);
+    op.end();
     return true;
 }
 
 template <typename LPH, int C>
 bool launch_env_split(const TimeGeom& G0, const float* din, float* dout, size_t smem_optin) {
     constexpr int H = LPH::N;
-    if (G0.nfft != 2 * H || G0.ntr % 4 != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) & 15) return false;
-    TimeGeom G = G0; G.C = C;
-    const long long tiles = (G.ntr + 2 * C - 1) / (2 * C);
-    if (tiles > 2147483647LL / (4 * C)) return false;
-    int box_rows, stage_rows;
-    pick_box(2 * H, C * (int)sizeof(float2), &box_rows, &stage_rows);
-    const size_t smem = (size_t)stage_rows * C * sizeof(float2) + (size_t)LPH::LINE * C * sizeof(Cx<float>) + 128;
-    if (smem > smem_optin - 1024) return false;
-    CUtensorMap map;
-    if (!tma_encode_tile_map(&map, din, 1, (int)G.nt, (int)(G.ntr / 2), 8, C, box_rows)) return false;
-    std::vector<int> rad(LPH::NPASS);
-    LPH::radices(rad.data());
-    std::vector<Cx<float>> t = spec_twiddle_table(rad);
-    const size_t woff = (t.size() + 1) & ~(size_t)1;
-    t.resize(woff + H);
-    for (int k = 0; k < H; ++k) {
-        const double a = -2.0 * M_PI * (double)k / (double)(2 * H);
-        t[woff + k] = cmake<float>((float)cos(a), (float)sin(a));
-    }
-    Cx<float>* d_tw = nullptr;
-    P3D_CUDA(cudaMalloc(&d_tw, sizeof(Cx<float>) * t.size()));
-    struct Free { Cx<float>* p; cudaEvent_t a, b; ~Free() { cudaFree(p); if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } fr{d_tw, nullptr, nullptr};
-    P3D_CUDA(cudaMemcpy(d_tw, t.data(), sizeof(Cx<float>) * t.size(), cudaMemcpyHostToDevice));
-    int dev = 0, sms = 0;
-    P3D_CUDA(cudaGetDevice(&dev));
-    P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (const char* g = getenv("P3D_TIME_GRID")) sms = std::max(1, atoi(g));
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sms);
-    P3D_CUDA(cudaEventCreate(&fr.a)); P3D_CUDA(cudaEventCreate(&fr.b));
-    P3D_CUDA(cudaEventRecord(fr.a, 0));
-    P3D_CUDA(cudaFuncSetAttribute(k_time_env_split<LPH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_time_env_split<LPH, C><<<grid, LPH::T * C, smem>>>(G, map, d_tw, d_tw + woff, dout, (int)tiles, box_rows, stage_rows);
-    P3D_CUDA(cudaGetLastError());
-    P3D_CUDA(cudaEventRecord(fr.b, 0));
-    P3D_CUDA(cudaDeviceSynchronize());
-    { float ms = 0.f; cudaEventElapsedTime(&ms, fr.a, fr.b); g_last_kernel_ms = ms; g_last_path = "tma"; }
+    if (G0.nfft != 2 * H) return false;
+    OnePass op;
+    if (!op.setup(G0, din, dout, C, 2 * H, G0.nt, (int)sizeof(float2), LPH::LINE, true, smem_optin)) return false;
+    op.tables(radices_of_plan<LPH>(), H);
+    op.begin(k_time_env_split<LPH, C>);
+    k_time_env_split<LPH, C><<<op.grid, LPH::T * C, op.smem>>>(op.G, op.map, op.d_tw, op.d_wsplit, dout, (int)op.tiles, op.box_rows, op.stage_rows);
+    op.end();
     return true;
 }
 
