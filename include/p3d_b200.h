@@ -183,6 +183,9 @@ int p3d_plan_describe(p3d_plan* plan, char* buf, int64_t buflen);
  *   "arena_cap"    support-record entries per slice (default 16384), "support_cap" largest support replayed per
  *                  iteration (0 = 2.2 sqrt(n_iline n_xline)), "pilot_min_elems" slices smaller than this skip the fp32
  *                  pilot (default 0), "fused_replay_max" largest support replayed by the one-launch kernel (1024), "seg_iters" iterations between two compactions of the fp32 slice list (4),
+ *   "lanes"        copy / compute lanes of the host-buffer path, each with its own stream, buffers and feeder thread
+ *                  (0 = default: 8, or 4 when LOCAL_WORLD_SIZE ranks x 8 spinning threads would exceed half of the host's
+ *                  hardware threads; device-resident data use one lane), "max_slices" largest chunk of slices per lane,
  *   "use_tma"      1 (default) / 0: column tiles fetched with cp.async.bulk.tensor where the tile shape allows it,
  *   "debug_fail_iter" testing only: the replay reports a failed verification at this iteration (-1 = off)} */
 int p3d_plan_set_option(p3d_plan* plan, const char* key, int64_t value);

@@ -1511,7 +1511,20 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     // one host: 8-11 GB/s per direction measured; e2e at 8 GPUs 444k -> 506k slice-it/s going from 2 to 4
     // lanes, 76.6k -> 80.9k on one GPU); device-resident data need one lane.
     // (the percentile operators share one scratch area and sort inside the iteration loop: one lane)
-    const int lanes = pr->thresh_percentile ? 1 : (P->n_lanes > 0 ? P->n_lanes : ((host_in || host_out) ? 4 : 1));
+    // (round 2, escalating mode: a chunk has several host waits - statistics, pilot verdict, list compaction -, and with
+    // 8 lanes of ~32 slices some lane always has kernels queued: e2e / device-resident 0.943 -> 0.961 on config 2,
+    // profiles/r2_sweep_e2e_chunks_v2.txt)
+    // Every lane has a feeder thread that spins in cudaStreamSynchronize: 8 lanes only while all ranks of this host
+    // (torchrun's LOCAL_WORLD_SIZE) keep that to half of the hardware threads - 4 lanes, round 1's setting, beyond.
+    int host_lanes = 8;
+    {
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lw ? std::max(1, atoi(lw)) : 1;
+        unsigned hc = std::thread::hardware_concurrency();
+        if (hc == 0) hc = 16;
+        if (2 * 8 * ranks > (int)hc) host_lanes = 4;
+    }
+    const int lanes = pr->thresh_percentile ? 1 : (P->n_lanes > 0 ? P->n_lanes : ((host_in || host_out) ? host_lanes : 1));
     if ((int)P->lanes.size() < lanes) P->lanes.resize(lanes);
     const int nbuf = 1 + (host_in ? 1 : 0) + (host_out ? 1 : 0) + (escalate ? 2 : 0);
     for (auto& L : P->lanes) { L.pending = false; L.n_escalated = 0; L.n_esc_iters = 0; L.n_verify_failed = 0; }
@@ -1527,10 +1540,11 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     if (lanes > 1) {
         const int64_t ne_ = (int64_t)P->n1 * P->n2;
         const int64_t min_chunk = std::max<int64_t>(1, std::min<int64_t>(n_slices, (int64_t)(48e6 / (8.0 * (double)ne_)) + 1));
-        // full-size chunks: ~2 per lane; the first and last chunks of a call are shorter (ramp below), so the
+        // full-size chunks: ~4 per lane (2 with 4 lanes); the first and last chunks of a call are shorter (ramp below), so the
         // un-overlapped first H2D / last D2H stay short while the bulk of the launches is large enough to keep
         // the tail of a launch (its last, partially filled wave of CTAs) small
-        want = std::max<int64_t>(min_chunk, (n_slices + 2 * lanes - 1) / (2 * lanes));
+        const int per_lane = lanes >= 8 ? 4 : 2;
+        want = std::max<int64_t>(min_chunk, (n_slices + per_lane * lanes - 1) / (per_lane * lanes));
     }
     if (P->max_slices > 0) want = std::min<int64_t>(want, P->max_slices);
     int64_t have = 0;
