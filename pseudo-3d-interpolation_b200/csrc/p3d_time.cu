@@ -507,6 +507,7 @@ k_time_fwd_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUt
             lo[e] = cmake<float>(p.x + t.x, p.y + t.y);          // Z[k]
             hi[e] = cmake<float>(p.x - t.x, p.y - t.y);          // Z[k + H]
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the parked values were written through the generic proxy; the refill is not
         __syncthreads();                                  // the stage is free: the next tile arrives during the epilogue
         issue(tile + gridDim.x);
         // separate the two real traces: rows k <= H need Z[N - k] = Z[(H - k) + H], the upper value of another thread
