@@ -619,6 +619,23 @@ def test_time_axis_paths(nt, shape, real, up, path, p3d, monkeypatch):
         assert rel_l2(xb, x[:nte]) < 5e-6
 
 
+@pytest.mark.parametrize("nt,ntr", [(2048, 20004), (1024, 30000), (2000, 12004)])
+def test_time_axis_one_pass_many_tiles_per_cta(nt, ntr, p3d):
+    """default path and grid (one persistent CTA per SM): every CTA walks over a dozen tiles; against numpy's rfft / irfft"""
+    from pseudo_3d_interpolation_b200 import timeaxis, synth, _lib
+    rng = np.random.default_rng(nt)
+    x = rng.standard_normal((nt, ntr)).astype(np.float32)
+    twt = synth.T0_MS + synth.DT_MS * np.arange(nt)
+    F, f = timeaxis.time_fft(x.reshape(nt, ntr, 1), twt, compute_real=True)
+    assert _lib.load().p3d_time_last_path().decode() == "tma"
+    ph = synth.DT_MS * np.exp(-2j * np.pi * f * synth.T0_MS)
+    Fr = np.fft.rfft(x.astype(np.float64), axis=0) * ph[:, None]
+    assert rel_l2(F[:, :, 0], Fr) < 5e-6
+    xb = timeaxis.time_ifft(F, synth.DT_MS, synth.T0_MS, compute_real=True, nt_out=nt)
+    assert _lib.load().p3d_time_last_path().decode() == "tma"
+    assert rel_l2(xb[:, :, 0], x) < 5e-6
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases
 # ------------------------------------------------------------------------------------------------
