@@ -122,7 +122,7 @@ template <typename T> struct BandArgs {
 
 // host: encode `map` for a (slices, n1, n2) array of complex values of `elem_bytes` bytes at `base`, box = C columns x
 // `rows` rows x 1 slice.  Returns false when the driver entry point is unavailable or rejects the shape.
-bool tma_encode_tile_map(CUtensorMap* map, const void* base, long long slices, int n1, int n2, int elem_bytes, int C, int rows);
+bool tma_encode_tile_map(CUtensorMap* map, const void* base, long long slices, int n1, int n2, int elem_bytes, int C, int rows, int row_step = 1);
 
 // internal operator of the complex128 column kernel: the tile already holds a thresholded spectrum (exact restart):
 // inverse transform only

@@ -453,7 +453,7 @@ k_time_inv_tma(const __grid_constant__ TimeGeom G, const __grid_constant__ CUten
 //   inverse (decimation in frequency):  x[2m] = IFFT_H(P[k] + P[k+H]),  x[2m+1] = IFFT_H((P[k] - P[k+H]) conj(w^k))
 // wsplit: w^k, k < H.
 // ------------------------------------------------------------------------------------------------
-template <typename LPH, int C>
+template <typename LPH, int C, bool PAR>
 __global__ void __launch_bounds__(LPH::T* C, 1)
 k_time_fwd_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUtensorMap tmap, const Cx<float>* __restrict__ tw,
                  const Cx<float>* __restrict__ wsplit, Cx<float>* __restrict__ F, const Cx<float>* __restrict__ phase,
@@ -462,8 +462,15 @@ k_time_fwd_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUt
     __shared__ unsigned long long bar;
     unsigned char* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     constexpr int E = LPH::E, T = LPH::T, H = LPH::N;
-    const int STAGE = stage_rows * C;
-    float2* stage = reinterpret_cast<float2*>(smem_raw);                    // [stage_rows >= 2H][C] trace pairs
+    // PAR (tiles of 64-byte rows): the tensor unit walks the box with a row step of 2, so the even samples land in rows
+    // [0, stage_rows) and the odd samples in rows [stage_rows, 2 stage_rows) (stage_rows >= H: whole boxes) and a warp
+    // reads 256 consecutive bytes of either half - with the samples interleaved as in the cube, the two rows a half-warp
+    // touches lie 128 bytes apart, a 2-way bank conflict on a quarter of the kernel's wavefronts (2.86 -> 3.04 TB/s at
+    // 2048 samples).  Tiles of 32-byte rows (4096 / 4000 samples) lose more to the doubled number of boxes: interleaved.
+    const int STAGE = (PAR ? 2 : 1) * stage_rows * C;
+    constexpr int ev_mul = PAR ? 1 : 2;                                     // even sample m: row ev_mul m, odd sample: od_off rows on
+    const int od_off = PAR ? stage_rows : 1;
+    float2* stage = reinterpret_cast<float2*>(smem_raw);                    // trace pairs
     const int tid = threadIdx.x;
     const int c = tid % C, j = tid / C;
     ColAcc1<float, C, LPH::LINE> acc; acc.base = reinterpret_cast<Cx<float>*>(smem_raw + (size_t)STAGE * sizeof(float2)) + c;
@@ -472,7 +479,14 @@ k_time_fwd_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUt
     auto issue = [&](int tile) {
         if (tid == 0 && tile < ntiles) {
             mbar_expect_tx(&bar, (unsigned)(STAGE * sizeof(float2)));
-            for (int r0 = 0; r0 < stage_rows; r0 += box_rows) tma_load_3d(stage + (size_t)r0 * C, &tmap, tile * C, r0, 0, &bar);
+            for (int r0 = 0; r0 < stage_rows; r0 += box_rows) {
+                if (PAR) {
+                    tma_load_3d(stage + (size_t)r0 * C, &tmap, tile * C, 2 * r0, 0, &bar);
+                    tma_load_3d(stage + (size_t)(stage_rows + r0) * C, &tmap, tile * C, 2 * r0 + 1, 0, &bar);
+                } else {
+                    tma_load_3d(stage + (size_t)r0 * C, &tmap, tile * C, r0, 0, &bar);
+                }
+            }
         }
     };
     const bool two_sided = G.nf > H + 1;
@@ -491,18 +505,18 @@ k_time_fwd_split(const __grid_constant__ TimeGeom G, const __grid_constant__ CUt
         asm volatile("" : "+l"(ws_t));
         Cx<float> lo[E], hi[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) { const float2 p = st[(2 * (j + e * T)) * C]; lo[e] = cmake<float>(p.x, p.y); }
+        for (int e = 0; e < E; ++e) { const float2 p = st[(ev_mul * (j + e * T)) * C]; lo[e] = cmake<float>(p.x, p.y); }
         LPH::template fft<-1, 0, float>(lo, acc, j, tw);
-        // park Ze[k] in the slots this thread has just emptied (row 2k of its own column)
+        // park Ze[k] in the slots this thread has just emptied (the even sample k of its own column)
 #pragma unroll
-        for (int e = 0; e < E; ++e) st[(2 * (j + e * T)) * C] = make_float2(lo[e].x, lo[e].y);
+        for (int e = 0; e < E; ++e) st[(ev_mul * (j + e * T)) * C] = make_float2(lo[e].x, lo[e].y);
 #pragma unroll
-        for (int e = 0; e < E; ++e) { const float2 p = st[(2 * (j + e * T) + 1) * C]; hi[e] = cmake<float>(p.x, p.y); }
+        for (int e = 0; e < E; ++e) { const float2 p = st[(ev_mul * (j + e * T) + od_off) * C]; hi[e] = cmake<float>(p.x, p.y); }
         LPH::template fft<-1, 0, float>(hi, acc, j, tw);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int k = j + e * T;
-            const float2 p = st[(2 * k) * C];
+            const float2 p = st[(ev_mul * k) * C];
             const Cx<float> t = cmul(hi[e], ws_t[k]);
             lo[e] = cmake<float>(p.x + t.x, p.y + t.y);          // Z[k]
             hi[e] = cmake<float>(p.x - t.x, p.y - t.y);          // Z[k + H]
@@ -1091,13 +1105,13 @@ bool launch_time_spec(const TimeGeom& G0, const void* din, void* dout, const Cx<
 
 // TMA boxes of a [rows x row_bytes] stage: at most 256 rows each and a multiple of 128 bytes (destination alignment);
 // the last box may reach beyond `rows` (zero-filled by the unit), so the stage holds stage_rows >= rows
-static void pick_box(int rows, int row_bytes, int* box_rows, int* stage_rows) {
+static void pick_box(int rows, int row_bytes, int* box_rows, int* stage_rows, int cap = 256) {
     int align = 1;
     while ((align * row_bytes) % 128) align *= 2;
-    for (int nbox = (rows + 255) / 256;; ++nbox) {
+    for (int nbox = (rows + cap - 1) / cap;; ++nbox) {
         int br = (rows + nbox - 1) / nbox;
         br = (br + align - 1) / align * align;
-        if (br <= 256) { *box_rows = br; *stage_rows = nbox * br; return; }
+        if (br <= cap) { *box_rows = br; *stage_rows = nbox * br; return; }
     }
 }
 
@@ -1118,18 +1132,19 @@ struct OnePass {
 
     // stage of `rows` rows of C elements (elem_bytes: 8 = a pair of samples, 16 = a pair of spectral values) cut out of a
     // (map_rows, n_traces / 2) tensor at `src`; `line` = exchange-buffer elements per line.  false: this path declines.
+    // parity: the even rows and the odd rows of the tile land in two halves of the stage (rows = rows per half)
     bool setup(const TimeGeom& G0, const void* src, const void* dst, int C, int rows, long long map_rows, int elem_bytes, int line,
-               bool use_tma, size_t smem_optin) {
+               bool use_tma, size_t smem_optin, bool parity = false) {
         if (G0.ntr % 4 != 0) return false;                                   // 16-byte row pitch and whole trace pairs
         if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return false;
         G = G0; G.C = C;
         tiles = (G.ntr + 2 * C - 1) / (2 * C);
         if (tiles > 2147483647LL / (4 * C)) return false;
-        pick_box(rows, C * elem_bytes, &box_rows, &stage_rows);
+        pick_box(rows, C * elem_bytes, &box_rows, &stage_rows, parity ? 128 : 256);
         if (!use_tma) stage_rows = rows;
-        smem = (size_t)stage_rows * C * elem_bytes + (size_t)line * C * sizeof(Cx<float>) + 128;
+        smem = (size_t)stage_rows * (parity ? 2 : 1) * C * elem_bytes + (size_t)line * C * sizeof(Cx<float>) + 128;
         if (smem > smem_optin - 1024) return false;
-        if (use_tma && !tma_encode_tile_map(&map, src, 1, (int)map_rows, (int)(G.ntr / 2), elem_bytes, C, box_rows)) return false;
+        if (use_tma && !tma_encode_tile_map(&map, src, 1, (int)map_rows, (int)(G.ntr / 2), elem_bytes, C, box_rows, parity ? 2 : 1)) return false;
         int dev = 0, sms = 0;
         P3D_CUDA(cudaGetDevice(&dev));
         P3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1193,12 +1208,13 @@ bool launch_time_split(const TimeGeom& G0, const void* din, void* dout, const Cx
     if (G0.nfft != 2 * H) return false;
     if (inverse && !G0.compute_real) return false;                       // a two-sided spectrum does not fit the stage
     OnePass op;
-    if (!inverse) { if (!op.setup(G0, din, dout, C, 2 * H, G0.nt, (int)sizeof(float2), LPH::LINE, true, smem_optin)) return false; }
+    constexpr bool PAR = C >= 8;                                         // even / odd halves of the stage (k_time_fwd_split)
+    if (!inverse) { if (!op.setup(G0, din, dout, C, PAR ? H : 2 * H, G0.nt, (int)sizeof(float2), LPH::LINE, true, smem_optin, PAR)) return false; }
     else          { if (!op.setup(G0, din, dout, C, H + 1, G0.nf, (int)sizeof(float4), LPH::LINE, true, smem_optin)) return false; }
     op.tables(radices_of_plan<LPH>(), H);
     if (!inverse) {
-        op.begin(k_time_fwd_split<LPH, C>);
-        k_time_fwd_split<LPH, C><<<op.grid, LPH::T * C, op.smem>>>(op.G, op.map, op.d_tw, op.d_wsplit, (Cx<float>*)dout, d_ph, (int)op.tiles, op.box_rows, op.stage_rows);
+        op.begin(k_time_fwd_split<LPH, C, PAR>);
+        k_time_fwd_split<LPH, C, PAR><<<op.grid, LPH::T * C, op.smem>>>(op.G, op.map, op.d_tw, op.d_wsplit, (Cx<float>*)dout, d_ph, (int)op.tiles, op.box_rows, op.stage_rows);
     } else {
         op.begin(k_time_inv_split<LPH, C>);
         k_time_inv_split<LPH, C><<<op.grid, LPH::T * C, op.smem>>>(op.G, op.map, op.d_tw, op.d_wsplit, (float*)dout, d_ph, (int)op.tiles, op.box_rows, op.stage_rows);
