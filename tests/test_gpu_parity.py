@@ -705,7 +705,8 @@ def test_edge_many_small_cubes_with_own_masks_and_early_exit(p3d):
 @pytest.mark.gpu
 def test_run_to_run_determinism_all_kernel_families():
     """every kernel family (register plans, mixed radix + Rader, generic + Bluestein, percentile, float64, kx-ky
-    filter, envelope, time axis) repeated on the same input: bit-identical results (tools/sanitize_cases.py)."""
+    filter, envelope, time axis incl. the one-pass TMA kernels) repeated on the same input: bit-identical results
+    (tools/sanitize_cases.py)."""
     import os
     import runpy
     import sys
@@ -715,7 +716,7 @@ def test_run_to_run_determinism_all_kernel_families():
         glb = runpy.run_path(os.path.join(root, "tools", "sanitize_cases.py"), run_name="__main__")
     finally:
         sys.argv = argv
-    assert glb["only"] == "all" and glb["CASES_RUN"] >= 16
+    assert glb["only"] == "all" and glb["CASES_RUN"] >= 17
 
 
 # ------------------------------------------------------------------------------------------------

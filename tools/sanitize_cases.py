@@ -2,7 +2,7 @@
 race or an out-of-bounds read shows up as run-to-run differences); also usable under compute-sanitizer where that
 is available:
 
-    python tools/sanitize_cases.py [spec|mix|generic|f64|aux]
+    python tools/sanitize_cases.py [spec|mix|generic|f64|aux|time]
     compute-sanitizer --tool racecheck python tools/sanitize_cases.py
 """
 import os
@@ -61,3 +61,27 @@ if only in ("all", "aux"):
         timeaxis.time_ifft(F, 0.05, 725.0, compute_real=True)
     CASES_RUN += 1
     print("ok aux", flush=True)
+if only in ("all", "time"):
+    # one-pass time-axis kernels (TMA-staged tiles; trace counts divisible by 4, two CTAs so that every CTA refills its stage)
+    grid_before = os.environ.get("P3D_TIME_GRID")
+    os.environ["P3D_TIME_GRID"] = "2"
+    rng = np.random.default_rng(1)
+    for nt, ntr in ((512, 136), (1000, 72), (1024, 72), (2048, 72), (2000, 40), (4096, 24), (4000, 24), (2500, 12)):
+        x = rng.standard_normal((nt, ntr)).astype(np.float32)
+        twt = 725.0 + 0.05 * np.arange(nt)
+        for real in (True, False):
+            F, _ = timeaxis.time_fft(x.reshape(nt, ntr, 1), twt, compute_real=real)
+            F2, _ = timeaxis.time_fft(x.reshape(nt, ntr, 1), twt, compute_real=real)
+            assert np.array_equal(F, F2)
+            Fin = F if real else np.fft.fftshift(F, axes=0)
+            y = timeaxis.time_ifft(Fin, 0.05, 725.0, compute_real=real)
+            assert np.array_equal(y, timeaxis.time_ifft(Fin, 0.05, 725.0, compute_real=real))
+            assert np.abs(y[:, :, 0] - x).max() < 1e-4
+        e = timeaxis.envelope(x, axis=0)
+        assert np.array_equal(e, timeaxis.envelope(x, axis=0))
+    if grid_before is None:
+        del os.environ["P3D_TIME_GRID"]
+    else:
+        os.environ["P3D_TIME_GRID"] = grid_before
+    CASES_RUN += 1
+    print("ok time", flush=True)
