@@ -1477,7 +1477,6 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
                     P3D_ERR_BAD_ARG, "Percentiles must be in the range [0, 100]");
         P3D_REQUIRE(pr->thresh_model == P3D_MODEL_LINEAR || pr->thresh_model == P3D_MODEL_EXPONENTIAL, P3D_ERR_NOT_IMPLEMENTED,
                     "percentile operators need a linear or exponential schedule of percentiles");
-        P3D_REQUIRE(P->precision != 64, P3D_ERR_NOT_IMPLEMENTED, "percentile operators run in the fp32 path only");
     }
     if (n_slices == 0) return P3D_OK;
     if (spm <= 0) spm = n_slices;
@@ -1489,7 +1488,10 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
     }
     DeviceGuard guard(P->device);
 
-    if (P->precision == 64 && !filt) {
+    // complex128 throughout: on request, and for the percentile operators in the default mode (every iteration thresholds at a
+    // data value - the percentile lies between two sorted moduli - so an fp32 iterate decides a near-tie differently
+    // sooner or later; there is no sparse support to replay either)
+    if ((P->precision == 64 || (P->precision == 0 && pr->thresh_percentile)) && !filt) {
         if (!P->f64) { P->f64 = f64_create(P->device, P->n1, P->n2, &P->ax1, &P->ax2, P->smem_optin); f64_install_spec(P->f64, P->spec_variant64); }
         f64_set_force_generic(P->f64, P->force_generic ? 1 : 0);
         if (P->lanes.empty()) P->lanes.resize(1);
@@ -1503,8 +1505,8 @@ int run_impl(p3d_plan* P, const p3d_pocs_params* pr, const void* x, int x_mem, c
                        cost_out, costs_out, tau_out, schedule_only, P->max_slices);
     }
     const bool host_in = x_mem == P3D_MEM_HOST, host_out = (out_mem == P3D_MEM_HOST) || schedule_only;
-    // escalating precision: every ordinary POCS run unless the plan was pinned to fp32 (the percentile operators and the
-    // kx-ky filter mode have no threshold decision that fp32 could get wrong / run in fp32 only)
+    // escalating precision: every ordinary POCS run unless the plan was pinned to fp32 (percentile operators: complex128
+    // above, or fp32 on request; the kx-ky filter mode has no threshold decision that fp32 could get wrong)
     const bool escalate = P->precision == 0 && !filt && !pr->thresh_percentile;
     // host data: four lanes (streams + buffer sets), each fed by its own host thread, so that the D2H of chunk i and the
     // H2D of chunk i+4 hide behind the iterations of chunks i+1..i+3 even when the PCIe path is slow (8 ranks sharing
@@ -1638,6 +1640,39 @@ void dd_schedule64_device(const Cx<double>* X0, long long ne, double lo_re, doub
     k_dd_keys64<<<std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(X0, ne, lo_re, lo_im, hi_re, hi_im, keys, vals, stats);
     cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, keys, keys + ne, vals, vals + ne, ne, 0, 64, st);
     k_pick_tau64<<<1, 128, 0, st>>>(keys + ne, vals + ne, X0, stats, tau64, niter);
+}
+
+// complex128 percentile operators: tau_sk holds the scheduled percentile q_k on entry and np.percentile(|X|, q_k) on exit
+// (numpy's 'linear' method: virtual index q / 100 (n - 1), _lerp between the two neighbours); keys: 2 * ne entries
+__global__ void k_abs_keys64(const Cx<double>* __restrict__ X, unsigned long long* __restrict__ keys, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const Cx<double> v = X[i];
+        keys[i] = (unsigned long long)__double_as_longlong(sqrt(v.x * v.x + v.y * v.y));      // non-negative doubles order like their bit patterns
+    }
+}
+__global__ void k_pick_percentile64(const unsigned long long* __restrict__ sorted, long long n, Cx<double>* tau_sk) {
+    const double q = tau_sk->x;
+    const double pos = q / 100.0 * (double)(n - 1);
+    long long lo = (long long)floor(pos);
+    lo = lo < 0 ? 0 : (lo > n - 1 ? n - 1 : lo);
+    const long long hi = lo + 1 > n - 1 ? n - 1 : lo + 1;
+    const double t = pos - (double)lo;
+    const double a = __longlong_as_double((long long)sorted[lo]), b = __longlong_as_double((long long)sorted[hi]);
+    const double diff = b - a;
+    double r = a + diff * t;
+    if (t >= 0.5) r = b - diff * (1.0 - t);
+    *tau_sk = cmake<double>(r, 0.0);
+}
+size_t percentile64_temp_bytes(long long ne) {
+    size_t need = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr, ne, 0, 64, (cudaStream_t)0);
+    return need;
+}
+void percentile64_device(const Cx<double>* X, long long ne, Cx<double>* tau_sk, unsigned long long* keys, void* temp, size_t temp_bytes,
+                         cudaStream_t st) {
+    k_abs_keys64<<<(unsigned)std::min<long long>((ne + 255) / 256, 148 * 8), 256, 0, st>>>(X, keys, ne);
+    cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys, keys + ne, ne, 0, 64, st);
+    k_pick_percentile64<<<1, 1, 0, st>>>(keys + ne, ne, tau_sk);
 }
 }  // namespace p3d
 

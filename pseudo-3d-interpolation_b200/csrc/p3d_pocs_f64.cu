@@ -28,6 +28,8 @@ struct F64Runner {
     uint32_t* mbits = nullptr; int64_t mbits_words = 0;
     int force_generic = 0;
     unsigned long long* dd_keys = nullptr; unsigned int* dd_vals = nullptr; void* dd_temp = nullptr; size_t dd_temp_bytes = 0; long long dd_ne = 0;
+    // percentile operators: spectra of a few slices, sort keys (2 ne) and sort scratch
+    Cx<double>* pct_scr = nullptr; int64_t pct_slices = 0; unsigned long long* pct_keys = nullptr; void* pct_temp = nullptr; size_t pct_temp_bytes = 0;
     std::vector<Cx<double>> h_tau; std::vector<double> h_S; std::vector<int> h_stop; std::vector<SliceStats> h_stats;
 };
 
@@ -99,6 +101,9 @@ void f64_destroy(F64Runner* R) {
     if (R->dd_keys) cudaFree(R->dd_keys);
     if (R->dd_vals) cudaFree(R->dd_vals);
     if (R->dd_temp) cudaFree(R->dd_temp);
+    if (R->pct_scr) cudaFree(R->pct_scr);
+    if (R->pct_keys) cudaFree(R->pct_keys);
+    if (R->pct_temp) cudaFree(R->pct_temp);
     if (R->st) cudaStreamDestroy(R->st);
     delete R;
 }
@@ -153,6 +158,32 @@ static void f64_ensure(F64Runner* R, int64_t n_slices, int niter, int64_t max_sl
 }
 
 // numpy ordering of complex numbers
+// percentile operators (threshold_operator.py:98-123 via functions/POCS.py:595-599): before iteration k the threshold of every
+// slice becomes np.percentile(|colFFT(W_s)|, q_k) - column transform of the band into a scratch area (the statistics
+// kernel with store_x0, W untouched), 64-bit radix sort of the moduli, linear interpolation between the two neighbours
+static void f64_percentile_thresholds(F64Runner* R, const AxisDev<double>& a1, const BandArgs<double>& B, int nb, int k, cudaStream_t st) {
+    const int64_t ne = (int64_t)R->n1 * R->n2;
+    if (!R->pct_scr) {
+        R->pct_slices = std::max<int64_t>(1, std::min<int64_t>(32, (int64_t)(256e6 / (16.0 * (double)ne))));
+        P3D_CUDA(cudaMalloc(&R->pct_scr, sizeof(Cx<double>) * ne * R->pct_slices));
+        P3D_CUDA(cudaMalloc(&R->pct_keys, sizeof(unsigned long long) * 2 * ne));
+        R->pct_temp_bytes = percentile64_temp_bytes(ne);
+        P3D_CUDA(cudaMalloc(&R->pct_temp, R->pct_temp_bytes));
+    }
+    for (int64_t s0 = 0; s0 < nb; s0 += R->pct_slices) {
+        const int cnt = (int)std::min<int64_t>(R->pct_slices, nb - s0);
+        BandArgs<double> Q = B;
+        Q.W = B.W + s0 * ne; Q.OUT = R->pct_scr; Q.stats = B.stats + s0; Q.stop = B.stop + s0; Q.S = B.S + s0 * (B.niter + 1);
+        Q.first_slice = B.first_slice + s0; Q.tau = B.tau + s0 * B.niter;
+        Q.adaptive = 0; Q.accum = 1; Q.store_x0 = 1;          // the statistics they also accumulate are not used any more
+        generic64_cols_stats(R->cfg, a1, Q, cnt, st);
+        for (int i = 0; i < cnt; ++i)
+            percentile64_device(R->pct_scr + (int64_t)i * ne, ne, const_cast<Cx<double>*>(B.tau) + (s0 + i) * B.niter + k, R->pct_keys,
+                                R->pct_temp, R->pct_temp_bytes, st);
+    }
+    P3D_CUDA(cudaGetLastError());
+}
+
 static inline bool lex_less(const cd& a, const cd& b) { return a.real() < b.real() || (a.real() == b.real() && a.imag() < b.imag()); }
 
 int f64_run(F64Runner* R, const p3d_pocs_params* prp, const Cx<float>* x, int x_mem, const uint8_t* dmask, int64_t spm,
@@ -285,6 +316,7 @@ int f64_run(F64Runner* R, const p3d_pocs_params* prp, const Cx<float>* x, int x_
             for (int k = 0; k < niter; ++k) {
                 B.k = k; B.last = (k == niter - 1) ? 1 : 0;
                 B.write_out = (B.last || (pr.eps > 0.0 && k >= 3)) ? 1 : 0;
+                if (pr.thresh_percentile) f64_percentile_thresholds(R, a1, B, nb, k, st);
                 if (spec_cols) R->spec.cols_iter(R->cfg.geom, R->tw_cols, B, nb, pr.thresh_op, st);
                 else generic64_cols_iter(R->cfg, a1, B, nb, pr.thresh_op, st);
                 if (spec_rows) R->spec.rows_iter(R->cfg.geom, R->tw_rows, B, nb, st);

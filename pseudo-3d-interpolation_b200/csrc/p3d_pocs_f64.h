@@ -26,6 +26,11 @@ void dd_schedule64_device(const Cx<double>* X0, long long ne, double lo_re, doub
                           Cx<double>* tau64, int niter, unsigned long long* keys, unsigned int* vals, void* temp, size_t temp_bytes,
                           cudaStream_t st);
 
+// percentile operators on complex128 state (p3d_pocs.cu): *tau_sk = np.percentile(|X|, tau_sk->x); keys: 2 * ne entries
+size_t percentile64_temp_bytes(long long ne);
+void percentile64_device(const Cx<double>* X, long long ne, Cx<double>* tau_sk, unsigned long long* keys, void* temp, size_t temp_bytes,
+                         cudaStream_t st);
+
 // ---- complex128 kernels for the escalating-precision engine (p3d_pocs.cu): the runner owns tile geometry, tables,
 // register plans and the packed mask of its row kernel; the engine owns the state buffers
 struct F64Kernels {
