@@ -1,12 +1,20 @@
-// Kernel 1: batched trace rfft / irfft along the time axis of a (nt, n_traces) cube.
+// Kernel 1: batched trace rfft / irfft / envelope along the time axis of a (nt, n_traces) cube.
 //
 // The time axis is the SLOWEST axis of the (twt, iline, xline) cube, so a trace is a strided
 // column.  A CTA takes a tile of 2C adjacent traces (contiguous 8C bytes per time sample),
 // packs two real traces into one complex line (z = x_a + i x_b), runs one complex FFT per
-// pair in shared memory and separates the two spectra with the Hermitian identities; the
-// epilogue applies dt * exp(-2 pi i f_k t0) * window[k] and writes the slice-major
-// (nf, n_traces) complex64 layout the POCS kernels consume.  The inverse does the mirror
-// image (phase, Hermitian symmetrisation = "take the real part", packed complex IFFT).
+// pair and separates the two spectra with the Hermitian identities; the epilogue applies
+// dt * exp(-2 pi i f_k t0) * window[k] and writes the slice-major (nf, n_traces) complex64
+// layout the POCS kernels consume.  The inverse does the mirror image (phase, Hermitian
+// symmetrisation = "take the real part", packed complex IFFT).
+//
+// Implementations, in the order try_time_spec() prefers them:
+//   k_time_{fwd,inv,env}_tma    one pass, persistent CTAs, TMA-staged tiles, register FFT (512 / 1000 / 1024 / 2500 samples)
+//   k_time_{fwd,inv,env}_split  the same with N = 2 H: two H-point register FFTs and a radix-2 step, tiles twice as wide
+//                               (2048 / 4096 / 2000 / 4000 samples)
+//   k_time_{fwd,inv}_spec       direct register kernels, plain loads, one tile per CTA
+//   k_transpose + k_time_*_rows transposing pipeline through L2 (any trace count / alignment)
+//   k_time_fwd / _inv / _env    generic shared-memory kernels (any record length, Bluestein included)
 #include "p3d_host.h"
 #include "p3d_fft_reg.cuh"
 #include "p3d_pocs_spec.cuh"
